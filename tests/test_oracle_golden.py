@@ -1,0 +1,134 @@
+"""The C restatement (oracle/) against the committed golden vectors, which were produced by
+running the reference itself (oracle/make_golden.py -> oracle/_ref/libccref.so, REF-FIXED).
+CPU only; this is what pins the oracle on machines without /root/reference."""
+import itertools
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import VARIANT_PARAMS, golden_H, load_golden
+
+BCH = ["bch_15_7", "bch_15_5", "bch_15_7_dmin5", "bch_15_7_dmin6", "bch_31_26", "bch_31_21", "bch_31_16",
+       "bch_31_11", "bch_63_57", "bch_63_51", "bch_63_45", "bch_63_39", "bch_63_36", "bch_127_120",
+       "bch_127_113", "bch_127_106", "bch_127_99", "bch_127_64", "bch_255_131"]
+RS = ["rs_7_5", "rs_7_3", "rs_15_9", "rs_255_223"]
+
+
+@pytest.mark.parametrize("q", range(1, 9))
+def test_gf_tables(q, golden_codes):
+    exp, log = oracle.gf_tables(q)
+    assert np.array_equal(exp, golden_codes["gf%d.exp" % q])
+    assert np.array_equal(log, golden_codes["gf%d.log" % q])
+
+
+@pytest.mark.parametrize("name", BCH + RS)
+def test_code_construction(name, catalogue, golden_codes):
+    e = catalogue[name]
+    c = oracle.Code(e["family"], e["q"], e["t"])
+    assert (c.n, c.l, c.k, c.dmin) == (e["n"], e["l"], e["k"], e["dmin"])
+    assert c.rate == e["rate"]
+    assert np.array_equal(c.poly("g"), golden_codes[name + ".g"])
+    assert np.array_equal(c.poly("h")[:c.deg_h + 1], golden_codes[name + ".h"])
+    if e["family"] == 0:
+        assert np.array_equal(c.H(), golden_H(golden_codes, catalogue, name))
+
+
+@pytest.mark.parametrize("name", ["bch_15_7", "bch_31_16", "bch_63_36", "bch_127_64", "bch_255_131"])
+def test_min_sum_golden(name, catalogue, golden_codes):
+    g = load_golden("minsum_%s.npz" % name)
+    H = golden_H(golden_codes, catalogue, name)
+    y = g["y"]
+    n = catalogue[name]["n"]
+    for v, (variant, alpha, beta, max_iter) in VARIANT_PARAMS.items():
+        if "v%d.iter" % v not in g:
+            continue
+        sel = slice(None) if n <= 63 else slice(0, 12)  # the dense restatement is O(k w n) per iteration
+        bits, L, it, failed = oracle.min_sum(H, y[sel], variant, alpha, beta, max_iter)
+        assert np.array_equal(failed, g["v%d.failed" % v][sel]), (name, v)
+        assert np.array_equal(it, g["v%d.iter" % v][sel]), (name, v)
+        ok = failed == 0
+        gb = np.unpackbits(g["v%d.bits" % v], axis=1)[sel, :n]
+        assert np.array_equal(bits[ok], gb[ok]), (name, v)
+        if "v%d.L" % v in g:
+            assert np.array_equal(L[ok].view(np.uint32), g["v%d.L" % v][sel][ok].view(np.uint32)), (name, v)
+
+
+@pytest.mark.parametrize("name", ["rs_255_223", "rs_15_9", "rs_7_3", "rs_7_5", "bch_15_7", "bch_31_16", "bch_63_36",
+                                  "bch_127_64", "bch_255_131"])
+def test_hard_golden(name, catalogue):
+    g = load_golden("hard_%s.npz" % name)
+    e = catalogue[name]
+    c = oracle.Code(e["family"], e["q"], e["t"])
+    assert np.array_equal(c.encode(g["msgs"]), g["words"])
+    out, nerr, status = c.hard_correct(g["received"])
+    assert np.array_equal(status, g["status"])
+    ok = status == 0
+    assert np.array_equal(out[ok], g["corrected"][ok])
+    # bounded-distance property of the golden data itself
+    within = g["nerr"] <= e["t"]
+    assert ok[within].all() and np.array_equal(out[within], g["words"][within])
+    assert ((out[ok] != g["received"][ok]).sum(axis=1) == nerr[ok]).all()
+
+
+def test_bitflip_table3(kat, catalogue, golden_codes):
+    """bitflips.c++ / report Table 3 on BCH(31,16,7): failures per error weight."""
+    H = golden_H(golden_codes, catalogue, "bch_31_16")
+    c = oracle.Code(0, 5, 3)
+    for w in range(0, 4):
+        pats = list(itertools.combinations(range(31), w))
+        y = np.ones((len(pats), 31), np.float32)
+        for i, pp in enumerate(pats):
+            y[i, list(pp)] = -1.0
+        row = kat["bitflip_31_16_7"][str(w)]
+        assert row["patterns"] == len(pats)
+        for v in (0, 1, 2, 3, 4, 5):
+            variant, alpha, beta, max_iter = VARIANT_PARAMS[v]
+            if w == 3 and v not in (0, 4):
+                continue  # keep the CPU suite short
+            bits, L, it, failed = oracle.min_sum(H, y, variant, alpha, beta, max_iter)
+            assert int(((failed == 1) | bits.any(axis=1)).sum()) == row[variant], (w, variant)
+        out, nerr, status = c.hard_correct((y < 0).astype(np.uint8))
+        assert int(((status != 0) | out.any(axis=1)).sum()) == row["EUKLID"]
+    # published percentages (report p.33) for the parameter-free decoders
+    for variant in ("MS", "SCMS2"):
+        for w in (2, 3):
+            row = kat["bitflip_31_16_7"][str(w)]
+            assert abs(100.0 * row[variant] / row["patterns"] - kat["table3_percent"][variant][w]) <= 0.1
+
+
+def test_exercises(kat, catalogue):
+    """exercises.c++ tasks 6.1-6.10 (errors-only and erasure cases) through the Euklid restatement."""
+    for key, ex in kat["exercises"].items():
+        e = catalogue[ex["code"]]
+        c = oracle.Code(e["family"], e["q"], e["t"])
+        if ex["alg"] == "PGZ" and ex["erasures"]:
+            continue
+        out, nerr, status = c.hard_correct(np.asarray([ex["received"]], np.uint8), ex["erasures"])
+        if ex["expect"] == "unspecified":
+            # bounded-distance decoders agree whenever both succeed
+            if status[0] == 0 and ex["status"] == 0:
+                assert list(map(int, out[0])) == ex["corrected"], key
+            continue
+        if ex["expect"] is None:
+            assert status[0] != 0, key
+        else:
+            assert status[0] == 0 and list(map(int, out[0])) == ex["expect"], key
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    assert [int(x) for x in oracle.philox4x32_10([0] * 4, [0] * 2)] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert [int(x) for x in oracle.philox4x32_10([0xffffffff] * 4, [0xffffffff] * 2)] == \
+        [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert [int(x) for x in oracle.philox4x32_10([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344],
+                                                 [0xa4093822, 0x299f31d0])] == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_channel_statistics():
+    y = oracle.awgn(seed=0, point=3, frame0=0, frames=4000, n=63, sigma_f=0.7)
+    z = (y.astype(np.float64) - 1.0) / 0.7
+    assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01
+    assert abs((np.abs(z) > 1.959964).mean() - 0.05) < 0.003
+    assert abs(oracle.sigma(36 / 63, 4.0) - 1 / np.sqrt(2 * 36 / 63 * 10 ** 0.4)) < 1e-7
