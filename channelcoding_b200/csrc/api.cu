@@ -1,0 +1,615 @@
+// api.cu -- the extern "C" boundary of libccgpu.so (include/ccgpu.h) and the host-side launch logic.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/ccgpu.h"
+#include "channel.cuh"
+#include "codes.hpp"
+#include "gf_decode.h"
+#include "ms_csr.h"
+#include "ms_params.h"
+
+using namespace ccgpu;
+
+// ------------------------------------------------------------------------------------------------
+struct ccgpu_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::mutex mu;
+  std::string err;
+  uint64_t launches = 0;
+  // device staging for host-pointer calls (grown on demand)
+  void *d_stage = nullptr;
+  size_t d_stage_bytes = 0;
+  unsigned long long *d_counters = nullptr;
+  ccgpu_counters *h_counters = nullptr;  // pinned
+};
+
+struct ccgpu_code {
+  ccgpu_ctx *ctx = nullptr;
+  CodeSpec spec;
+  HShape shape;
+  // min-sum kernel selection for SC = 0 / 1
+  const MsCyclicEntry *cyc[2] = { nullptr, nullptr };
+  int fpw[2] = { 1, 1 };
+  int grid_max[2] = { 0, 0 };
+  size_t smem[2] = { 0, 0 };
+  MsCsrDevice csr;     // general-H kernel tables (device)
+  GfDevice gf;         // algebraic decoder tables (device)
+};
+
+namespace {
+
+int fail(ccgpu_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+int cuda_fail(ccgpu_ctx *ctx, cudaError_t e, const char *what) {
+  return fail(ctx, CCGPU_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                                    \
+  do {                                                              \
+    cudaError_t e_ = (call);                                        \
+    if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);        \
+  } while (0)
+
+bool is_device_ptr(const void *p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure_stage(ccgpu_ctx *ctx, size_t bytes) {
+  if (bytes <= ctx->d_stage_bytes) return CCGPU_OK;
+  if (ctx->d_stage) cudaFree(ctx->d_stage);
+  ctx->d_stage = nullptr;
+  ctx->d_stage_bytes = 0;
+  const size_t want = std::max(bytes, size_t(1) << 20);
+  CU(cudaMalloc(&ctx->d_stage, want));
+  ctx->d_stage_bytes = want;
+  return CCGPU_OK;
+}
+
+// K1: one thread = one Philox block = four consecutive symbols of one frame.  The tile of
+// kTileFrames frames is assembled in shared memory and leaves the SM as coalesced 16-byte stores.
+constexpr int kAwgnThreads = 256;
+__global__ void __launch_bounds__(kAwgnThreads) awgn_llr_kernel(float *__restrict__ y, uint32_t n, float sigma,
+                                                               uint64_t seed, uint32_t point, uint64_t frame0,
+                                                               uint64_t frames, uint32_t tile_frames) {
+  extern __shared__ float tile[];
+  const uint32_t nblk = (n + 3) >> 2;
+  const uint64_t tiles = (frames + tile_frames - 1) / tile_frames;
+  for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const uint64_t f0 = t * tile_frames;
+    const uint32_t nf = static_cast<uint32_t>(min(static_cast<uint64_t>(tile_frames), frames - f0));
+    for (uint32_t b = threadIdx.x; b < nf * nblk; b += blockDim.x) {
+      const uint32_t f = b / nblk, blk = b - f * nblk;
+      const float4 v = awgn_block(seed, point, frame0 + f0 + f, blk, sigma);
+      float *dst = tile + f * n + 4 * blk;
+      const float vv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (4 * blk + e < n) dst[e] = vv[e];
+    }
+    __syncthreads();
+    const uint64_t base = f0 * n;              // multiple of 4 floats because tile_frames % 4 == 0
+    const uint32_t total = nf * n;
+    float4 *out4 = reinterpret_cast<float4 *>(y + base);
+    const float4 *in4 = reinterpret_cast<const float4 *>(tile);
+    for (uint32_t i = threadIdx.x; i < total / 4; i += blockDim.x) __stcs(out4 + i, in4[i]);
+    for (uint32_t i = (total & ~3u) + threadIdx.x; i < total; i += blockDim.x) y[base + i] = tile[i];
+    __syncthreads();
+  }
+}
+
+// pick the cyclic kernel instantiation for this H (nullptr: none fits -> CSR kernel)
+void select_cyclic(ccgpu_code *c) {
+  for (int sc = 0; sc < 2; ++sc) c->cyc[sc] = nullptr;
+  if (c->shape.kind > 1 || c->shape.taps.empty()) return;
+  const int n = static_cast<int>(c->spec.n), k = static_cast<int>(c->spec.rows);
+  const int w = static_cast<int>(c->shape.taps.size());
+  const int wrap = c->shape.kind;
+  if (w > kMaxTaps) return;
+  for (int sc = 0; sc < 2; ++sc) {
+    long best_score = -1;
+    for (int i = 0, m = ms_cyclic_count(); i < m; ++i) {
+      const MsCyclicEntry *e = ms_cyclic_at(i);
+      if (e->w != w || e->sc != sc || e->wrap < wrap || e->rpl * 32 < k || 32 * e->np < n) continue;
+      int fpw = 1;
+      if (e->rpl == 1) fpw = std::max(1, std::min({ 32 / k, 4, (32 * e->np) / n }));
+      // prefer: exact wrap, fewer rows per lane, more frames per warp, fewer passes
+      const long score = (e->wrap == wrap ? 1000000 : 0) + (8 - e->rpl) * 10000 + fpw * 100 + (16 - e->np);
+      if (score > best_score) {
+        best_score = score;
+        c->cyc[sc] = e;
+        c->fpw[sc] = fpw;
+      }
+    }
+    if (c->cyc[sc]) {
+      c->smem[sc] = size_t(kMsThreads / 32) * 2 * 32 * c->cyc[sc]->np * sizeof(float);
+      int occ = 0;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void *>(c->cyc[sc]->fn),
+                                                    kMsThreads, c->smem[sc]);
+      c->grid_max[sc] = std::max(1, occ) * c->ctx->sm_count;
+    }
+  }
+}
+
+int finish_code(ccgpu_ctx *ctx, ccgpu_code *c) {
+  c->ctx = ctx;
+  c->shape = analyse_H(c->spec.H.data(), c->spec.rows, c->spec.n);
+  if (!ctx) return CCGPU_OK;  // host-only description: no device tables, no decoding
+  select_cyclic(c);
+  int rc = ms_csr_upload(c->spec.H.data(), c->spec.rows, c->spec.n, &c->csr);
+  if (rc != 0) return fail(ctx, CCGPU_ERR_CUDA, "ms_csr_upload failed");
+  if (c->spec.family != 2) {
+    rc = gf_upload(c->spec, &c->gf);
+    if (rc != 0) return fail(ctx, CCGPU_ERR_CUDA, "gf_upload failed");
+  }
+  return CCGPU_OK;
+}
+
+int check_params(ccgpu_ctx *ctx, const ccgpu_ms_params *p) {
+  if (!p) return fail(ctx, CCGPU_ERR_INVALID, "params is null");
+  if (p->variant < CCGPU_MS || p->variant > CCGPU_SPA) return fail(ctx, CCGPU_ERR_INVALID, "unknown variant");
+  if (p->stop_rule < 0 || p->stop_rule > CCGPU_STOP_NONE) return fail(ctx, CCGPU_ERR_INVALID, "unknown stop rule");
+  if (p->max_iter < 1 || p->max_iter > 255) return fail(ctx, CCGPU_ERR_INVALID, "max_iter must be in 1..255");
+  if (p->variant == CCGPU_OMS && !(p->beta >= 0.0)) return fail(ctx, CCGPU_ERR_INVALID, "OMS needs beta >= 0");
+  return CCGPU_OK;
+}
+
+// fills the decoder part of a parameter block
+void fill_decoder(MsParams &mp, const ccgpu_code *c, const ccgpu_ms_params *p) {
+  mp.n = static_cast<int>(c->spec.n);
+  mp.k = static_cast<int>(c->spec.rows);
+  mp.variant = p->variant;
+  mp.stop_rule = p->stop_rule;
+  mp.max_iter = static_cast<int>(p->max_iter);
+  mp.alpha_f = static_cast<float>(p->alpha);  // double -> float where the reference's functor call does
+  mp.beta_f = static_cast<float>(p->beta);
+  mp.beta_d = p->beta;
+}
+
+// launch the min-sum decoder for one batch described by mp (source/outputs already filled)
+int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsParams mp) {
+  if (mp.frames == 0) return CCGPU_OK;
+  const int sc = (p->variant == CCGPU_SCMS1 || p->variant == CCGPU_SCMS2) ? 1 : 0;
+  if (p->variant != CCGPU_SPA && c->cyc[sc]) {
+    const MsCyclicEntry *e = c->cyc[sc];
+    mp.w = e->w;
+    mp.fpw = c->fpw[sc];
+    for (int j = 0; j < e->w; ++j) mp.tap[j] = static_cast<int16_t>(c->shape.taps[j]);
+    const uint64_t per_cta = uint64_t(kMsThreads / 32) * mp.fpw;
+    const uint64_t want = (mp.frames + per_cta - 1) / per_cta;
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(want, c->grid_max[sc]));
+    void *args[] = { &mp };
+    CU(cudaLaunchKernel(reinterpret_cast<const void *>(e->fn), dim3(grid), dim3(kMsThreads), args, c->smem[sc],
+                        ctx->stream));
+    ctx->launches++;
+    return CCGPU_OK;
+  }
+  int rc = ms_csr_launch(c->csr, mp, ctx->sm_count, ctx->stream);
+  if (rc == -3) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "parity-check matrix too large for the CSR kernel");
+  if (rc != 0) return cuda_fail(ctx, cudaGetLastError(), "ms_csr_launch");
+  ctx->launches++;
+  return CCGPU_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int ccgpu_abi_version(void) { return CCGPU_ABI_VERSION; }
+
+int ccgpu_create(int device, ccgpu_ctx **out) {
+  if (!out) return CCGPU_ERR_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return CCGPU_ERR_NO_DEVICE;
+  }
+  ccgpu_ctx *ctx = new ccgpu_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+      cudaMalloc(&ctx->d_counters, sizeof(ccgpu_counters)) != cudaSuccess ||
+      cudaMallocHost(&ctx->h_counters, sizeof(ccgpu_counters)) != cudaSuccess) {
+    cudaGetLastError();
+    delete ctx;
+    return CCGPU_ERR_CUDA;
+  }
+  *out = ctx;
+  return CCGPU_OK;
+}
+
+void ccgpu_destroy(ccgpu_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->d_stage) cudaFree(ctx->d_stage);
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *ccgpu_last_error(const ccgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+
+int ccgpu_set_stream(ccgpu_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return CCGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (ctx->own_stream && ctx->stream) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamDestroy(ctx->stream);
+  }
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  ctx->own_stream = false;
+  return CCGPU_OK;
+}
+void *ccgpu_get_stream(ccgpu_ctx *ctx) { return ctx ? static_cast<void *>(ctx->stream) : nullptr; }
+
+int ccgpu_sync(ccgpu_ctx *ctx) {
+  if (!ctx) return CCGPU_ERR_INVALID;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return CCGPU_OK;
+}
+uint64_t ccgpu_kernel_launches(const ccgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- codes -------------------------------------------------------------------------------------
+static int make_code(ccgpu_ctx *ctx, CodeSpec &&spec, ccgpu_code **out) {
+  ccgpu_code *c = new ccgpu_code();
+  c->spec = std::move(spec);
+  if (ctx) cudaSetDevice(ctx->device);
+  const int rc = finish_code(ctx, c);
+  if (rc != CCGPU_OK) {
+    ccgpu_code_destroy(c);
+    return rc;
+  }
+  *out = c;
+  return CCGPU_OK;
+}
+
+int ccgpu_bch_create(ccgpu_ctx *ctx, uint32_t q, int cap_kind, uint32_t cap_value, ccgpu_code **out) {
+  if (!out) return CCGPU_ERR_INVALID;
+  std::unique_lock<std::mutex> g;
+  if (ctx) g = std::unique_lock<std::mutex>(ctx->mu);
+  try {
+    return make_code(ctx, make_bch(q, cap_kind, cap_value), out);
+  } catch (const std::exception &e) {
+    return fail(ctx, CCGPU_ERR_INVALID, e.what());
+  }
+}
+
+int ccgpu_rs_create(ccgpu_ctx *ctx, uint32_t q, uint32_t t, uint32_t mu, uint32_t step, ccgpu_code **out) {
+  if (!out) return CCGPU_ERR_INVALID;
+  std::unique_lock<std::mutex> g;
+  if (ctx) g = std::unique_lock<std::mutex>(ctx->mu);
+  try {
+    return make_code(ctx, make_rs(q, t, mu, step), out);
+  } catch (const std::exception &e) {
+    return fail(ctx, CCGPU_ERR_INVALID, e.what());
+  }
+}
+
+int ccgpu_code_from_dense(ccgpu_ctx *ctx, const uint8_t *H, uint32_t rows, uint32_t cols, double rate, ccgpu_code **out) {
+  if (!out || !H || rows == 0 || cols == 0) return CCGPU_ERR_INVALID;
+  std::unique_lock<std::mutex> g;
+  if (ctx) g = std::unique_lock<std::mutex>(ctx->mu);
+  CodeSpec s;
+  s.family = 2;
+  s.n = cols;
+  s.rows = rows;
+  s.k = rows;
+  s.l = cols > rows ? cols - rows : 0;
+  s.rate = rate;
+  s.H.assign(H, H + size_t(rows) * cols);
+  for (auto &v : s.H) v = v ? 1 : 0;
+  return make_code(ctx, std::move(s), out);
+}
+
+int ccgpu_code_set_rows(ccgpu_code *code, uint32_t rows) {
+  if (!code) return CCGPU_ERR_INVALID;
+  ccgpu_ctx *ctx = code->ctx;
+  std::unique_lock<std::mutex> g;
+  if (ctx) g = std::unique_lock<std::mutex>(ctx->mu);
+  try {
+    if (rows < code->spec.k) return fail(ctx, CCGPU_ERR_INVALID, "rows must be >= k");
+    code->spec.set_rows(rows);
+  } catch (const std::exception &e) {
+    return fail(ctx, CCGPU_ERR_INVALID, e.what());
+  }
+  code->shape = analyse_H(code->spec.H.data(), code->spec.rows, code->spec.n);
+  if (!ctx) return CCGPU_OK;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  ms_csr_free(&code->csr);
+  code->shape = analyse_H(code->spec.H.data(), code->spec.rows, code->spec.n);
+  select_cyclic(code);
+  if (ms_csr_upload(code->spec.H.data(), code->spec.rows, code->spec.n, &code->csr) != 0)
+    return fail(ctx, CCGPU_ERR_CUDA, "ms_csr_upload failed");
+  return CCGPU_OK;
+}
+
+void ccgpu_code_destroy(ccgpu_code *code) {
+  if (!code) return;
+  if (code->ctx) {
+    cudaSetDevice(code->ctx->device);
+    cudaStreamSynchronize(code->ctx->stream);
+  }
+  ms_csr_free(&code->csr);
+  gf_free(&code->gf);
+  delete code;
+}
+
+int ccgpu_code_get_info(const ccgpu_code *code, ccgpu_code_info *out) {
+  if (!code || !out) return CCGPU_ERR_INVALID;
+  std::memset(out, 0, sizeof(*out));
+  const CodeSpec &s = code->spec;
+  out->family = s.family;
+  out->q = s.q;
+  out->n = s.n;
+  out->l = s.l;
+  out->k = s.k;
+  out->dmin = s.dmin;
+  out->t = s.t;
+  out->h_rows = s.rows;
+  out->row_weight = code->shape.max_row_weight;
+  out->edges = code->shape.edges;
+  out->h_kind = code->shape.kind;
+  out->kernel = !code->ctx ? 0 : (code->cyc[0] ? 1 : 2);
+  out->rate = s.rate;
+  return CCGPU_OK;
+}
+
+int ccgpu_code_to_string(const ccgpu_code *code, const char *tag, char *buf, size_t cap) {
+  if (!code || !buf || cap == 0) return CCGPU_ERR_INVALID;
+  std::snprintf(buf, cap, "%s", code->spec.to_string(tag ? tag : "").c_str());
+  return CCGPU_OK;
+}
+
+int ccgpu_code_H(const ccgpu_code *code, uint8_t *out) {
+  if (!code || !out) return CCGPU_ERR_INVALID;
+  std::memcpy(out, code->spec.H.data(), code->spec.H.size());
+  return CCGPU_OK;
+}
+
+int ccgpu_code_poly(const ccgpu_code *code, int which, uint16_t *out, size_t cap) {
+  if (!code || !out) return CCGPU_ERR_INVALID;
+  const Poly &p = which ? code->spec.h : code->spec.g;
+  if (p.size() > cap) return CCGPU_ERR_INVALID;
+  std::copy(p.begin(), p.end(), out);
+  return static_cast<int>(p.size());
+}
+
+int ccgpu_gf_tables(uint32_t q, uint32_t poly, uint16_t *exp_out, uint16_t *log_out) {
+  if (!exp_out || !log_out) return CCGPU_ERR_INVALID;
+  try {
+    Field F(q, poly);
+    std::copy(F.exp.begin(), F.exp.end(), exp_out);
+    std::copy(F.log.begin(), F.log.end(), log_out);
+  } catch (const std::exception &) {
+    return CCGPU_ERR_INVALID;
+  }
+  return CCGPU_OK;
+}
+
+int ccgpu_encode(const ccgpu_code *code, const uint8_t *msgs, uint64_t count, uint8_t *words) {
+  if (!code || !msgs || !words || code->spec.family == 2) return CCGPU_ERR_INVALID;
+  try {
+    for (uint64_t i = 0; i < count; ++i) code->spec.encode(msgs + i * code->spec.l, words + i * code->spec.n);
+  } catch (const std::exception &e) {
+    return fail(code->ctx, CCGPU_ERR_INVALID, e.what());
+  }
+  return CCGPU_OK;
+}
+
+double ccgpu_sigma(double rate, double ebno_db) {
+  // simulation.c++:83-85 evaluates 1.0f / sqrt(2 R 10^(EbN0/10)) in double
+  return 1.0f / std::sqrt(2 * rate * std::pow(10, ebno_db / 10.0));
+}
+
+// ---- decoding ----------------------------------------------------------------------------------
+int ccgpu_decode_llr(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, const float *y,
+                     uint64_t frames, uint8_t *bits, float *L, uint8_t *iter, uint8_t *failed) {
+  if (!ctx || !code || !y || !bits || !failed) return fail(ctx, CCGPU_ERR_INVALID, "null argument");
+  if (code->ctx != ctx) return fail(ctx, CCGPU_ERR_INVALID, "code was not created on this context");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  int rc = check_params(ctx, params);
+  if (rc) return rc;
+  if (frames == 0) return CCGPU_OK;
+  CU(cudaSetDevice(ctx->device));
+  const size_t n = code->spec.n;
+  MsParams mp{};
+  fill_decoder(mp, code, params);
+  mp.src = SRC_HBM;
+  mp.frames = frames;
+  const bool dev = is_device_ptr(y);
+  if (dev) {
+    if (!is_device_ptr(bits) || !is_device_ptr(failed) || (L && !is_device_ptr(L)) || (iter && !is_device_ptr(iter)))
+      return fail(ctx, CCGPU_ERR_INVALID, "y is a device pointer: every output must be one too");
+    mp.y = y;
+    mp.bits = bits;
+    mp.L = L;
+    mp.iter = iter;
+    mp.failed = failed;
+    return launch_ms(ctx, code, params, mp);
+  }
+  // host buffers: stage in chunks so H2D of chunk i+1 can overlap the decode of chunk i
+  const size_t per_frame = n * sizeof(float) + n + (L ? n * sizeof(float) : 0) + 2;
+  const uint64_t chunk = std::min<uint64_t>(frames, std::max<uint64_t>(1, (size_t(256) << 20) / per_frame));
+  rc = ensure_stage(ctx, chunk * per_frame + 64);
+  if (rc) return rc;
+  char *base = static_cast<char *>(ctx->d_stage);
+  float *d_y = reinterpret_cast<float *>(base);
+  float *d_L = L ? reinterpret_cast<float *>(base + chunk * n * sizeof(float)) : nullptr;
+  uint8_t *d_bits = reinterpret_cast<uint8_t *>(base + chunk * n * sizeof(float) * (L ? 2 : 1));
+  uint8_t *d_iter = d_bits + chunk * n;
+  uint8_t *d_failed = d_iter + chunk;
+  for (uint64_t f0 = 0; f0 < frames; f0 += chunk) {
+    const uint64_t nf = std::min(chunk, frames - f0);
+    CU(cudaMemcpyAsync(d_y, y + f0 * n, nf * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    mp.y = d_y;
+    mp.bits = d_bits;
+    mp.L = d_L;
+    mp.iter = d_iter;
+    mp.failed = d_failed;
+    mp.frames = nf;
+    rc = launch_ms(ctx, code, params, mp);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(bits + f0 * n, d_bits, nf * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (L) CU(cudaMemcpyAsync(L + f0 * n, d_L, nf * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (iter) CU(cudaMemcpyAsync(iter + f0, d_iter, nf, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(failed + f0, d_failed, nf, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return CCGPU_OK;
+}
+
+int ccgpu_awgn_llr(ccgpu_ctx *ctx, uint32_t n, double sigma, uint64_t seed, uint32_t point, uint64_t frame0,
+                   uint64_t frames, float *y) {
+  if (!ctx || !y || n == 0) return fail(ctx, CCGPU_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (frames == 0) return CCGPU_OK;
+  CU(cudaSetDevice(ctx->device));
+  const bool dev = is_device_ptr(y);
+  float *d_y = y;
+  if (!dev) {
+    const int rc = ensure_stage(ctx, frames * n * sizeof(float));
+    if (rc) return rc;
+    d_y = static_cast<float *>(ctx->d_stage);
+  }
+  if (reinterpret_cast<uintptr_t>(d_y) % 16 != 0) return fail(ctx, CCGPU_ERR_INVALID, "y must be 16-byte aligned");
+  // tile: a multiple of 4 frames (keeps every tile base 16-byte aligned), about 32 KB
+  uint32_t tile_frames = std::max<uint32_t>(4, (8192 / n) & ~3u);
+  const size_t smem = size_t(tile_frames) * n * sizeof(float);
+  const uint64_t tiles = (frames + tile_frames - 1) / tile_frames;
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, uint64_t(ctx->sm_count) * 8));
+  CU(cudaFuncSetAttribute(awgn_llr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  awgn_llr_kernel<<<grid, kAwgnThreads, smem, ctx->stream>>>(d_y, n, static_cast<float>(sigma), seed, point, frame0,
+                                                            frames, tile_frames);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  if (!dev) {
+    CU(cudaMemcpyAsync(y, d_y, frames * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  return CCGPU_OK;
+}
+
+static int counted_launch(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, MsParams mp,
+                          ccgpu_counters *out) {
+  const bool dev = is_device_ptr(out);
+  if (dev) {
+    mp.counters = reinterpret_cast<unsigned long long *>(out);
+    return launch_ms(ctx, code, params, mp);
+  }
+  CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(ccgpu_counters), ctx->stream));
+  mp.counters = ctx->d_counters;
+  const int rc = launch_ms(ctx, code, params, mp);
+  if (rc) return rc;
+  CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(ccgpu_counters), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *out = *ctx->h_counters;
+  return CCGPU_OK;
+}
+
+int ccgpu_awgn_point(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, double ebno_db,
+                     uint64_t seed, uint32_t point, uint64_t frame0, uint64_t frames, ccgpu_counters *out) {
+  if (!ctx || !code || !out) return fail(ctx, CCGPU_ERR_INVALID, "null argument");
+  if (code->ctx != ctx) return fail(ctx, CCGPU_ERR_INVALID, "code was not created on this context");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  int rc = check_params(ctx, params);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  MsParams mp{};
+  fill_decoder(mp, code, params);
+  mp.src = SRC_PHILOX;
+  mp.sigma = static_cast<float>(ccgpu_sigma(code->spec.rate, ebno_db));  // simulation.c++:113-115
+  mp.seed = seed;
+  mp.point = point;
+  mp.frame0 = frame0;
+  mp.frames = frames;
+  return counted_launch(ctx, code, params, mp, out);
+}
+
+int ccgpu_bitflip_point(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, uint32_t weight,
+                        uint64_t first, uint64_t count, ccgpu_counters *out) {
+  if (!ctx || !code || !out) return fail(ctx, CCGPU_ERR_INVALID, "null argument");
+  if (code->ctx != ctx) return fail(ctx, CCGPU_ERR_INVALID, "code was not created on this context");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  int rc = check_params(ctx, params);
+  if (rc) return rc;
+  const unsigned n = code->spec.n;
+  if (weight > n) return fail(ctx, CCGPU_ERR_INVALID, "weight > n");
+  long double total = 1;
+  for (unsigned i = 1; i <= weight; ++i) total = total * (n - weight + i) / i;
+  if (total > 1.8e19L) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "C(n, weight) does not fit 64 bits");
+  const uint64_t patterns = static_cast<uint64_t>(total + 0.5L);
+  if (first > patterns) return fail(ctx, CCGPU_ERR_INVALID, "first > C(n, weight)");
+  if (count == 0 || count > patterns - first) count = patterns - first;
+  CU(cudaSetDevice(ctx->device));
+  MsParams mp{};
+  fill_decoder(mp, code, params);
+  mp.src = SRC_BITFLIP;
+  mp.flip_weight = weight;
+  mp.frame0 = first;
+  mp.frames = count;
+  return counted_launch(ctx, code, params, mp, out);
+}
+
+int ccgpu_gf_decode(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8_t *words, uint64_t count,
+                    uint8_t *corrected, uint8_t *n_errors, uint8_t *failed) {
+  if (!ctx || !code || !words || !corrected || !failed) return fail(ctx, CCGPU_ERR_INVALID, "null argument");
+  if (code->ctx != ctx) return fail(ctx, CCGPU_ERR_INVALID, "code was not created on this context");
+  if (code->spec.family == 2) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "algebraic decoding needs a BCH/RS code");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (count == 0) return CCGPU_OK;
+  CU(cudaSetDevice(ctx->device));
+  const size_t n = code->spec.n;
+  const bool dev = is_device_ptr(words);
+  if (dev) {
+    if (!is_device_ptr(corrected) || !is_device_ptr(failed) || (n_errors && !is_device_ptr(n_errors)))
+      return fail(ctx, CCGPU_ERR_INVALID, "words is a device pointer: every output must be one too");
+    if (gf_launch(code->gf, words, count, corrected, n_errors, failed, ctx->sm_count, ctx->stream) != 0)
+      return cuda_fail(ctx, cudaGetLastError(), "gf_launch");
+    ctx->launches++;
+    return CCGPU_OK;
+  }
+  const size_t per_word = 2 * n + 2;
+  const uint64_t chunk = std::min<uint64_t>(count, std::max<uint64_t>(1, (size_t(256) << 20) / per_word));
+  int rc = ensure_stage(ctx, chunk * per_word + 64);
+  if (rc) return rc;
+  uint8_t *d_in = static_cast<uint8_t *>(ctx->d_stage);
+  uint8_t *d_out = d_in + chunk * n;
+  uint8_t *d_ne = d_out + chunk * n;
+  uint8_t *d_fail = d_ne + chunk;
+  for (uint64_t w0 = 0; w0 < count; w0 += chunk) {
+    const uint64_t nw = std::min(chunk, count - w0);
+    CU(cudaMemcpyAsync(d_in, words + w0 * n, nw * n, cudaMemcpyHostToDevice, ctx->stream));
+    if (gf_launch(code->gf, d_in, nw, d_out, d_ne, d_fail, ctx->sm_count, ctx->stream) != 0)
+      return cuda_fail(ctx, cudaGetLastError(), "gf_launch");
+    ctx->launches++;
+    CU(cudaMemcpyAsync(corrected + w0 * n, d_out, nw * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n_errors) CU(cudaMemcpyAsync(n_errors + w0, d_ne, nw, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(failed + w0, d_fail, nw, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return CCGPU_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,367 @@
+// ms_cyclic.cuh -- K2: flooding min-sum decoder for cyclic parity-check matrices, sm_100a.
+//
+// Replaces  min_sum__<Iterations,U,R,Q>(H, y, hor, vert)   reference codes/soft_decision.h:161-202
+// (vertical__ :125-140, horizontal__ :101-122, column_sum :86-98, syndrome :79-84) for H built by
+// cyclic::H<T>() (codes/cyclic.h:346-359): row r has its ones at columns r + tap[j].
+//
+// Mapping (one warp owns FPW frames; nothing but the final decisions/counters leaves the SM):
+//   * lane <-> parity-check ROW.  The row's W edge messages r[j] live in REGISTERS for the whole
+//     decode (W is a template parameter, loops fully unrolled, tap offsets come from the
+//     __grid_constant__ parameter block = constant bank operands).
+//   * per frame only y[n] and the column sums S[n] live in shared memory (2n floats).
+//   * VN+CN pass: q_j = (S[c_j] - r_j) + y[c_j] exactly as soft_decision.h:135-136; min1/min2 and
+//     the sign parity are reduced IN the lane (a row is private to a lane: no shuffles), then
+//     r_j = +-fn_h(min over the others) (:106-118).
+//   * column sums in the reference's order (rows ascending, :86-98): all lanes step through the
+//     taps from the largest to the smallest and add r_j into S[row + tap_j]; within one step the
+//     32 columns are distinct (conflict free), and a column receives its rows in ascending order
+//     because row = column - tap.  One __syncwarp per step keeps that order.
+//   * hard decision + stop test: lane <-> column, __ballot_sync gives the decided word as bit
+//     masks, every row-lane popcounts its row mask against it (integer overlap mod 256 for the
+//     reference's rule, parity for GF(2)).
+//   * frames finish after different iteration counts: every frame group of a warp carries its own
+//     iteration counter and refills itself from a grid-strided frame sequence (persistent warps).
+//
+// Float semantics: additions/multiplications are the explicit _rn intrinsics
+// so nothing is contracted into FMAs; the OMS offset is applied in double; signum(0) = 0 is
+// honoured because a zero among "the others" forces min = 0 and fn_h(0) = 0.
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "channel.cuh"
+#include "ms_params.h"
+
+namespace ccgpu {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ float xor_sign(float v, unsigned signbits) {
+  return __uint_as_float(__float_as_uint(v) ^ (signbits & 0x80000000u));
+}
+
+// fn_h of the variant applied to a non-negative minimum (soft_decision.h:204-213, :245-251)
+__device__ __forceinline__ float cn_magnitude(const MsParams &p, float m) {
+  if (p.variant == V_NMS || p.variant == V_NMS2D) return __fmul_rn(p.alpha_f, m);
+  if (p.variant == V_OMS) {
+    const double d = static_cast<double>(m) - p.beta_d;
+    return static_cast<float>(d > 0.0 ? d : 0.0);
+  }
+  return m;
+}
+
+// lexicographic unranking of the `rank`-th length-n 0/1 sequence with `w` ones in the order of
+// std::next_permutation starting from 0..01..1 (simulation.c++:181-199); returns bit of column c
+__device__ __forceinline__ unsigned long long binom(unsigned n, unsigned r) {
+  if (r > n) return 0ull;
+  unsigned long long v = 1ull;
+  for (unsigned i = 1; i <= r; ++i) v = v * (n - r + i) / i;
+  return v;
+}
+
+template <int W, int RPL, int NP, bool SC, bool WRAP>
+__global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_constant__ MsParams p) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp_in_cta = threadIdx.x >> 5;
+  const int n = p.n, k = p.k, fpw = p.fpw;
+  const int items = fpw * n;  // <= 32 * NP columns handled by this warp
+  float *ybuf = smem + warp_in_cta * (2 * 32 * NP);
+  float *sbuf = ybuf + 32 * NP;
+
+  // ---------------- row-lane mapping
+  int grp = 0;
+  int row[RPL];
+  bool rvalid[RPL];
+  if (RPL == 1) {
+    grp = lane / k;
+    row[0] = lane - grp * k;
+    rvalid[0] = grp < fpw;
+    if (!rvalid[0]) grp = 0;  // idle lanes shadow group 0's control flow, touch nothing
+  } else {
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      row[i] = lane + 32 * i;
+      rvalid[i] = row[i] < k;
+    }
+  }
+  const int colbase = grp * n;
+  const int lead_lane = (RPL == 1) ? grp * k : 0;  // lane that speaks for the group
+  const bool is_lead = (lane == lead_lane) && rvalid[0];
+  const unsigned gmask = (RPL == 1) ? ((k >= 32 ? kFull : ((1u << k) - 1u)) << lead_lane) : kFull;
+
+  // ---------------- column-lane mapping: item c = lane + 32*pass  ->  (frame group, column)
+  int cgrp_lead[NP];   // lead lane of the group that owns item c
+  int ccol[NP];        // column inside the frame
+  bool cvalid[NP];
+  unsigned cmask[NP];  // bits of the concatenated decision word that belong to MY group
+#pragma unroll
+  for (int ps = 0; ps < NP; ++ps) {
+    const int c = lane + 32 * ps;
+    cvalid[ps] = c < items;
+    const int f = (RPL == 1 && cvalid[ps]) ? c / n : 0;
+    ccol[ps] = c - f * n;
+    cgrp_lead[ps] = (RPL == 1) ? f * k : 0;
+    // my group's columns occupy [colbase, colbase + n) of the concatenated word
+    const int lo = colbase - 32 * ps, hi = colbase + n - 32 * ps;
+    unsigned m = 0;
+    if (hi > 0 && lo < 32) {
+      const int a = lo < 0 ? 0 : lo, b = hi > 32 ? 32 : hi;
+      m = (b - a >= 32) ? kFull : (((1u << (b - a)) - 1u) << a);
+    }
+    cmask[ps] = m;
+  }
+
+  // ---------------- row masks for the stop test (bit = colbase + column)
+  unsigned rmask[RPL][NP];
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) {
+#pragma unroll
+    for (int ps = 0; ps < NP; ++ps) rmask[i][ps] = 0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      int c = row[i] + p.tap[j];
+      if (WRAP && c >= n) c -= n;
+      c += colbase;
+#pragma unroll
+      for (int ps = 0; ps < NP; ++ps)
+        if ((c >> 5) == ps && rvalid[i]) rmask[i][ps] |= 1u << (c & 31);
+    }
+  }
+
+  // ---------------- per-group decode state (replicated in every lane of the group)
+  const long long warps_total = static_cast<long long>(gridDim.x) * (kMsThreads / 32);
+  const long long units = warps_total * fpw;
+  long long my_frame = (static_cast<long long>(blockIdx.x) * (kMsThreads / 32) + warp_in_cta) * fpw + grp;
+  bool active = my_frame < static_cast<long long>(p.frames);
+  bool need_init = true;
+  int it = 0;
+  float r[RPL][W];
+  float qold[SC ? RPL : 1][SC ? W : 1];
+  unsigned long long cnt_frames = 0, cnt_ferr = 0, cnt_berr = 0, cnt_iter = 0, cnt_fail = 0, cnt_und = 0;
+
+  const bool is2d = p.variant == V_NMS2D;
+  const int nblk = (n + 3) >> 2;
+
+  while (true) {
+    if (__ballot_sync(kFull, active) == 0u) break;
+
+    // ============ (re)fill frame groups that finished
+    const unsigned initm = __ballot_sync(kFull, active && need_init);
+    if (initm) {
+      if (p.src == SRC_HBM) {
+#pragma unroll
+        for (int ps = 0; ps < NP; ++ps) {
+          const long long fr = __shfl_sync(kFull, my_frame, cgrp_lead[ps]);
+          if (cvalid[ps] && ((initm >> cgrp_lead[ps]) & 1u)) {
+            ybuf[lane + 32 * ps] = __ldg(p.y + fr * n + ccol[ps]);
+            sbuf[lane + 32 * ps] = 0.0f;
+          }
+        }
+      } else if (p.src == SRC_PHILOX) {
+        for (int b0 = 0; b0 < fpw * nblk; b0 += 32) {
+          const int b = b0 + lane;
+          const bool bv = b < fpw * nblk;
+          const int f = (RPL == 1 && bv) ? b / nblk : 0;
+          const int blk = b - f * nblk;
+          const int src_lane = (RPL == 1) ? f * k : 0;
+          const long long fr = __shfl_sync(kFull, my_frame, src_lane);
+          if (bv && ((initm >> src_lane) & 1u)) {
+            const float4 v = awgn_block(p.seed, p.point, p.frame0 + static_cast<uint64_t>(fr), blk, p.sigma);
+            const int c0 = f * n + 4 * blk;
+            const float vv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (4 * blk + e < n) {
+                ybuf[c0 + e] = vv[e];
+                sbuf[c0 + e] = 0.0f;
+              }
+          }
+        }
+      } else {  // SRC_BITFLIP: x = -2*bit + 1 for the pattern of lexicographic rank frame0 + fr
+        if (is_lead && active && need_init) {
+          unsigned long long rank = p.frame0 + static_cast<unsigned long long>(my_frame);
+          unsigned ones = p.flip_weight;
+          for (int c = 0; c < n; ++c) {
+            const unsigned long long zero_first = binom(n - c - 1, ones);
+            float v = 1.0f;
+            if (rank >= zero_first && ones > 0) {
+              rank -= zero_first;
+              --ones;
+              v = -1.0f;
+            }
+            ybuf[colbase + c] = v;
+            sbuf[colbase + c] = 0.0f;
+          }
+        }
+      }
+      if (active && need_init) {
+#pragma unroll
+        for (int i = 0; i < RPL; ++i)
+#pragma unroll
+          for (int j = 0; j < W; ++j) {
+            r[i][j] = 0.0f;
+            if (SC) qold[i][j] = 0.0f;
+          }
+        it = 0;
+        need_init = false;
+      }
+      __syncwarp();
+    }
+
+    // ============ VN + CN  (vertical__ / horizontal__)
+    float f1s[RPL], f2s[RPL], m1v[RPL];
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      float m1 = FLT_MAX, m2 = FLT_MAX;
+      unsigned par = 0;
+      if (rvalid[i]) {
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          int c = row[i] + p.tap[j];
+          if (WRAP && c >= n) c -= n;
+          c += colbase;
+          const float s = sbuf[c];
+          const float yy = ybuf[c];
+          float e = __fsub_rn(s, r[i][j]);        // exclusive column sum (:135)
+          if (is2d) e = __fmul_rn(p.beta_f, e);   // normalised_vertical (:215-218)
+          float q = __fadd_rn(e, yy);             // unmodified_vertical (:205-209)
+          if (SC) {
+            const float qo = qold[i][j];
+            if (p.variant == V_SCMS1) {            // :261-267
+              const bool keep = (qo == 0.0f) || ((qo > 0.0f) == (q > 0.0f) && (qo < 0.0f) == (q < 0.0f));
+              q = keep ? q : 0.0f;
+            } else {                               // SCMS2 :275-281
+              q = (__fmul_rn(q, qo) > 0.0f) ? q : __fmul_rn(0.5f, __fadd_rn(q, qo));
+            }
+            qold[i][j] = q;
+          } else {
+            r[i][j] = q;  // r_j is dead once q_j exists; reuse its register
+          }
+          const float a = fabsf(q);
+          m2 = fminf(m2, fmaxf(m1, a));
+          m1 = fminf(m1, a);
+          par ^= __float_as_uint(q);
+        }
+      }
+      m1v[i] = m1;
+      f1s[i] = xor_sign(cn_magnitude(p, m1), par);  // fold the row's sign parity in once
+      f2s[i] = xor_sign(cn_magnitude(p, m2), par);
+    }
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        const float q = SC ? qold[i][j] : r[i][j];
+        // min over the others is min2 exactly for the edge(s) attaining min1 (ties: min2 == min1)
+        const float f = (fabsf(q) == m1v[i]) ? f2s[i] : f1s[i];
+        r[i][j] = xor_sign(f, __float_as_uint(q));  // sign = prod of the other signs (:114,:118)
+      }
+    }
+    __syncwarp();
+
+    // ============ column sums, rows ascending (column_sum :86-98)
+#pragma unroll
+    for (int ps = 0; ps < NP; ++ps)
+      if (cvalid[ps]) sbuf[lane + 32 * ps] = 0.0f;
+    __syncwarp();
+#pragma unroll
+    for (int pass = 0; pass < (WRAP ? 2 : 1); ++pass) {
+#pragma unroll
+      for (int j = W - 1; j >= 0; --j) {
+#pragma unroll
+        for (int i = 0; i < RPL; ++i) {
+          int c = row[i] + p.tap[j];
+          bool wrapped = false;
+          if (WRAP && c >= n) {
+            c -= n;
+            wrapped = true;
+          }
+          if (rvalid[i] && wrapped == (pass == 1)) {
+            c += colbase;
+            sbuf[c] = __fadd_rn(sbuf[c], r[i][j]);
+          }
+        }
+        __syncwarp();
+      }
+    }
+
+    // ============ totals, hard decision (:178-183), stop test (:79-84)
+    unsigned bw[NP];
+#pragma unroll
+    for (int ps = 0; ps < NP; ++ps) {
+      bool neg = false;
+      if (cvalid[ps]) neg = __fadd_rn(sbuf[lane + 32 * ps], ybuf[lane + 32 * ps]) < 0.0f;
+      bw[ps] = __ballot_sync(kFull, neg);
+    }
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < RPL; ++i) {
+      int ov = 0;
+#pragma unroll
+      for (int ps = 0; ps < NP; ++ps) ov += __popc(bw[ps] & rmask[i][ps]);
+      if (rvalid[i]) {
+        if (p.stop_rule == STOP_REF) bad |= (ov & 255) != 0;
+        else if (p.stop_rule == STOP_GF2) bad |= (ov & 1) != 0;
+        else bad = true;
+      }
+    }
+    const unsigned badm = __ballot_sync(kFull, bad);
+    const bool stop = (badm & gmask) == 0u;
+    const bool last = it + 1 >= p.max_iter;
+    const bool fin = active && !need_init && (stop || last);
+    const unsigned finm = __ballot_sync(kFull, fin);
+    if (finm) {
+      // ---- decided word / totals of the finishing groups
+      if (p.bits != nullptr || p.L != nullptr) {
+#pragma unroll
+        for (int ps = 0; ps < NP; ++ps) {
+          const long long fr = __shfl_sync(kFull, my_frame, cgrp_lead[ps]);
+          if (cvalid[ps] && ((finm >> cgrp_lead[ps]) & 1u)) {
+            if (p.bits) p.bits[fr * n + ccol[ps]] = static_cast<uint8_t>((bw[ps] >> lane) & 1u);
+            if (p.L) p.L[fr * n + ccol[ps]] = __fadd_rn(sbuf[lane + 32 * ps], ybuf[lane + 32 * ps]);
+          }
+        }
+      }
+      if (fin) {
+        const bool failed = !stop && p.stop_rule != STOP_NONE;
+        int nbits = 0;
+#pragma unroll
+        for (int ps = 0; ps < NP; ++ps) nbits += __popc(bw[ps] & cmask[ps]);
+        if (is_lead) {
+          if (p.iter) p.iter[my_frame] = static_cast<uint8_t>(failed ? p.max_iter : it);
+          if (p.failed) p.failed[my_frame] = failed ? 1 : 0;
+          cnt_frames += 1;
+          cnt_iter += static_cast<unsigned>(it + 1);
+          cnt_fail += failed ? 1 : 0;
+          cnt_berr += static_cast<unsigned>(nbits);
+          cnt_ferr += (failed || nbits != 0) ? 1 : 0;
+          cnt_und += (!failed && nbits != 0) ? 1 : 0;
+        }
+        my_frame += units;
+        active = my_frame < static_cast<long long>(p.frames);
+        need_init = true;
+      }
+    }
+    if (!fin) ++it;
+  }
+
+  // ---------------- counters: warp reduce, one atomic per slot per warp
+  if (p.counters != nullptr) {
+    unsigned long long v[6] = { cnt_frames, cnt_ferr, cnt_berr, cnt_iter, cnt_fail, cnt_und };
+#pragma unroll
+    for (int s = 0; s < 6; ++s) {
+      unsigned long long x = v[s];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(kFull, x, o);
+      if (lane == 0 && x) atomicAdd(p.counters + s, x);
+    }
+  }
+}
+
+#define CCGPU_MS_CYCLIC_ENTRY(W, RPL, NP, SC, WRAP)                                                    \
+  { W, RPL, NP, SC, WRAP, reinterpret_cast<ms_kernel_fn>(&ms_cyclic_kernel<W, RPL, NP, (SC) != 0, (WRAP) != 0>), \
+    "ms_cyclic<W=" #W ",RPL=" #RPL ",NP=" #NP ",SC=" #SC ",WRAP=" #WRAP ">" }
+
+}  // namespace ccgpu

@@ -1,0 +1,48 @@
+// ms_registry.cu -- lookup over the kernel instantiation groups (ms_cyclic_inst.cu x CCGPU_GROUP).
+#include "ms_cyclic_list.h"
+#include "ms_params.h"
+
+namespace ccgpu {
+
+#define CCGPU_DECL(g) const MsCyclicEntry *ms_cyclic_group_##g(int *count);
+CCGPU_DECL(0) CCGPU_DECL(1) CCGPU_DECL(2) CCGPU_DECL(3) CCGPU_DECL(4) CCGPU_DECL(5) CCGPU_DECL(6) CCGPU_DECL(7)
+#undef CCGPU_DECL
+static_assert(CCGPU_MS_GROUPS == 8, "update the declarations above");
+
+using group_fn = const MsCyclicEntry *(*)(int *);
+static const group_fn kGroups[CCGPU_MS_GROUPS] = { ms_cyclic_group_0, ms_cyclic_group_1, ms_cyclic_group_2,
+                                                   ms_cyclic_group_3, ms_cyclic_group_4, ms_cyclic_group_5,
+                                                   ms_cyclic_group_6, ms_cyclic_group_7 };
+
+int ms_cyclic_count() {
+  int total = 0;
+  for (group_fn g : kGroups) {
+    int c = 0;
+    g(&c);
+    total += c;
+  }
+  return total;
+}
+
+const MsCyclicEntry *ms_cyclic_at(int i) {
+  for (group_fn g : kGroups) {
+    int c = 0;
+    const MsCyclicEntry *e = g(&c);
+    if (i < c) return e + i;
+    i -= c;
+  }
+  return nullptr;
+}
+
+// smallest registered shape that can run (w, rpl) with at least np passes
+const MsCyclicEntry *ms_cyclic_find(int w, int rpl, int np, int sc, int wrap) {
+  const MsCyclicEntry *best = nullptr;
+  for (int i = 0, m = ms_cyclic_count(); i < m; ++i) {
+    const MsCyclicEntry *e = ms_cyclic_at(i);
+    if (e->w != w || e->rpl != rpl || e->sc != sc || e->wrap != wrap || e->np < np) continue;
+    if (!best || e->np < best->np) best = e;
+  }
+  return best;
+}
+
+}  // namespace ccgpu

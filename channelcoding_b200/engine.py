@@ -1,0 +1,269 @@
+"""Thin object layer over the C ABI (include/ccgpu.h): Context (one CUDA device + stream) and Code
+(a BCH / RS code or a dense parity-check matrix uploaded to the device).
+
+Array arguments may be numpy arrays (host path: staged through the library, call returns when the
+results are in the output arrays) or torch CUDA tensors (device path: enqueued on the context's
+stream, no synchronisation)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import CcgpuError, CodeInfo, Counters, MsParams
+
+VARIANTS = {"MS": 0, "NMS": 1, "OMS": 2, "SCMS1": 3, "SCMS2": 4, "2DNMS": 5, "SPA": 6}
+STOP_REF_ZERO_OVERLAP, STOP_GF2_PARITY, STOP_NONE = 0, 1, 2
+CAP_ERRORS, CAP_DMIN = 0, 1
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if _is_torch(x):
+        assert x.is_contiguous()
+        return x.data_ptr()
+    assert x.flags["C_CONTIGUOUS"]
+    return x.ctypes.data
+
+
+def ms_params(variant="MS", alpha=1.0, beta=0.0, max_iter=50, stop_rule=STOP_REF_ZERO_OVERLAP):
+    v = VARIANTS[variant] if isinstance(variant, str) else int(variant)
+    return MsParams(v, int(stop_rule), int(max_iter), 0, float(alpha), float(beta))
+
+
+def _check(ctx, rc):
+    if rc != 0:
+        if ctx is not None:
+            ctx._check(rc)
+        raise CcgpuError(rc, "call failed (host-only code)")
+
+
+def host_bch(q, errors=None, dmin=None):
+    """host-only description of cyclic::primitive_bch<q, ..> (no CUDA device needed, no decoding)"""
+    assert (errors is None) != (dmin is None)
+    h = C.c_void_p()
+    kind, val = (CAP_ERRORS, errors) if errors is not None else (CAP_DMIN, dmin)
+    _check(None, _lib.lib().ccgpu_bch_create(None, q, kind, val, C.byref(h)))
+    return Code(None, h)
+
+
+def host_rs(q, errors, mu=1, step=1):
+    h = C.c_void_p()
+    _check(None, _lib.lib().ccgpu_rs_create(None, q, errors, mu, step, C.byref(h)))
+    return Code(None, h)
+
+
+def host_from_dense(H, rate):
+    H = np.ascontiguousarray(H, np.uint8)
+    h = C.c_void_p()
+    _check(None, _lib.lib().ccgpu_code_from_dense(None, H.ctypes.data, H.shape[0], H.shape[1], float(rate), C.byref(h)))
+    return Code(None, h)
+
+
+class Context:
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = _lib.lib().ccgpu_create(int(device), C.byref(self._h))
+        if rc != 0:
+            raise CcgpuError(rc, "ccgpu_create(device=%d) failed -- no usable CUDA device; there is no CPU "
+                                 "fallback" % device)
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().ccgpu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CcgpuError(rc, _lib.lib().ccgpu_last_error(self._h).decode())
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(_lib.lib().ccgpu_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def use_torch_stream(self):
+        import torch
+        self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def sync(self):
+        self._check(_lib.lib().ccgpu_sync(self._h))
+
+    @property
+    def kernel_launches(self):
+        return int(_lib.lib().ccgpu_kernel_launches(self._h))
+
+    # ---- codes
+    def bch(self, q, errors=None, dmin=None):
+        """cyclic::primitive_bch<q, errors<e>> / <q, dmin<d>> (codes/bch.h:16-161)"""
+        assert (errors is None) != (dmin is None)
+        h = C.c_void_p()
+        kind, val = (CAP_ERRORS, errors) if errors is not None else (CAP_DMIN, dmin)
+        self._check(_lib.lib().ccgpu_bch_create(self._h, q, kind, val, C.byref(h)))
+        return Code(self, h)
+
+    def rs(self, q, errors, mu=1, step=1):
+        """cyclic::rs<q, errors<e>, .., mu, step> (codes/rs.h:6-94)"""
+        h = C.c_void_p()
+        self._check(_lib.lib().ccgpu_rs_create(self._h, q, errors, mu, step, C.byref(h)))
+        return Code(self, h)
+
+    def from_dense(self, H, rate):
+        H = np.ascontiguousarray(H, np.uint8)
+        h = C.c_void_p()
+        self._check(_lib.lib().ccgpu_code_from_dense(self._h, H.ctypes.data, H.shape[0], H.shape[1], float(rate),
+                                                     C.byref(h)))
+        return Code(self, h)
+
+    # ---- channel
+    def awgn_llr(self, n, sigma, seed, point, frame0, frames, out=None):
+        if out is None:
+            out = np.empty((frames, n), np.float32)
+        self._check(_lib.lib().ccgpu_awgn_llr(self._h, n, float(sigma), seed, point, frame0, frames, _ptr(out)))
+        return out
+
+
+class Code:
+    def __init__(self, ctx, handle):
+        self.ctx = ctx
+        self._h = handle
+        self._refresh()
+
+    def _refresh(self):
+        info = CodeInfo()
+        _check(self.ctx, _lib.lib().ccgpu_code_get_info(self._h, C.byref(info)))
+        for k, _ in CodeInfo._fields_:
+            setattr(self, k, getattr(info, k))
+
+    def close(self):
+        if getattr(self, "_h", None) and (self.ctx is None or getattr(self.ctx, "_h", None)):
+            _lib.lib().ccgpu_code_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def to_string(self, tag):
+        buf = C.create_string_buffer(128)
+        _check(self.ctx, _lib.lib().ccgpu_code_to_string(self._h, tag.encode(), buf, 128))
+        return buf.value.decode()
+
+    def H(self):
+        out = np.zeros((self.h_rows, self.n), np.uint8)
+        _check(self.ctx, _lib.lib().ccgpu_code_H(self._h, out.ctypes.data))
+        return out
+
+    def poly(self, which):
+        out = np.zeros(1024, np.uint16)
+        m = _lib.lib().ccgpu_code_poly(self._h, {"g": 0, "h": 1}[which], out.ctypes.data, 1024)
+        if m < 0:
+            raise CcgpuError(m, "ccgpu_code_poly")
+        return out[:m].copy()
+
+    def set_rows(self, rows):
+        _check(self.ctx, _lib.lib().ccgpu_code_set_rows(self._h, rows))
+        self._refresh()
+
+    def encode(self, msgs):
+        msgs = np.ascontiguousarray(msgs, np.uint8).reshape(-1, self.l)
+        words = np.zeros((msgs.shape[0], self.n), np.uint8)
+        _check(self.ctx, _lib.lib().ccgpu_encode(self._h, msgs.ctypes.data, msgs.shape[0], words.ctypes.data))
+        return words
+
+    # ---- decoding
+    def decode(self, y, variant="MS", alpha=1.0, beta=0.0, max_iter=50, stop_rule=STOP_REF_ZERO_OVERLAP, want_L=True,
+               out=None):
+        """min_sum<float,uint8_t>(H, y, Tag{}) per frame -> bits, L, iter, failed (ccgpu_decode_llr)"""
+        p = ms_params(variant, alpha, beta, max_iter, stop_rule)
+        if _is_torch(y):
+            import torch
+            y = y.contiguous().view(-1, self.n)
+            frames = y.shape[0]
+            if out is None:
+                bits = torch.empty((frames, self.n), dtype=torch.uint8, device=y.device)
+                L = torch.empty((frames, self.n), dtype=torch.float32, device=y.device) if want_L else None
+                it = torch.empty(frames, dtype=torch.uint8, device=y.device)
+                failed = torch.empty(frames, dtype=torch.uint8, device=y.device)
+            else:
+                bits, L, it, failed = out
+        else:
+            y = np.ascontiguousarray(y, np.float32).reshape(-1, self.n)
+            frames = y.shape[0]
+            if out is None:
+                bits = np.empty((frames, self.n), np.uint8)
+                L = np.empty((frames, self.n), np.float32) if want_L else None
+                it = np.empty(frames, np.uint8)
+                failed = np.empty(frames, np.uint8)
+            else:
+                bits, L, it, failed = out
+        self.ctx._check(_lib.lib().ccgpu_decode_llr(self.ctx._h, self._h, C.byref(p), _ptr(y), frames, _ptr(bits),
+                                                    _ptr(L), _ptr(it), _ptr(failed)))
+        return bits, L, it, failed
+
+    def awgn_point(self, ebno_db, frames, variant="MS", alpha=1.0, beta=0.0, max_iter=50,
+                   stop_rule=STOP_REF_ZERO_OVERLAP, seed=0, point=0, frame0=0, out=None):
+        """one Eb/N0 point of awgn_simulation (simulation.c++:112-149), fused on the GPU -> counters.
+        out: optional torch uint64/int64 CUDA tensor of 8 slots that is accumulated into (no sync)."""
+        p = ms_params(variant, alpha, beta, max_iter, stop_rule)
+        if out is not None:
+            self.ctx._check(_lib.lib().ccgpu_awgn_point(self.ctx._h, self._h, C.byref(p), float(ebno_db), seed, point,
+                                                        frame0, frames, _ptr(out)))
+            return out
+        c = Counters()
+        self.ctx._check(_lib.lib().ccgpu_awgn_point(self.ctx._h, self._h, C.byref(p), float(ebno_db), seed, point,
+                                                    frame0, frames, C.addressof(c)))
+        return c.as_dict()
+
+    def bitflip_point(self, weight, variant="MS", alpha=1.0, beta=0.0, max_iter=50,
+                      stop_rule=STOP_REF_ZERO_OVERLAP, first=0, count=0):
+        """one error weight of bitflip_simulation (simulation.c++:156-213) -> counters"""
+        p = ms_params(variant, alpha, beta, max_iter, stop_rule)
+        c = Counters()
+        self.ctx._check(_lib.lib().ccgpu_bitflip_point(self.ctx._h, self._h, C.byref(p), weight, first, count,
+                                                       C.addressof(c)))
+        return c.as_dict()
+
+    def gf_decode(self, words, out=None):
+        """cyclic::correct_(.., hard_decision_tag) per word -> corrected, n_errors, failed"""
+        if _is_torch(words):
+            import torch
+            words = words.contiguous().view(-1, self.n)
+            cnt = words.shape[0]
+            if out is None:
+                out = (torch.empty_like(words), torch.empty(cnt, dtype=torch.uint8, device=words.device),
+                       torch.empty(cnt, dtype=torch.uint8, device=words.device))
+        else:
+            words = np.ascontiguousarray(words, np.uint8).reshape(-1, self.n)
+            cnt = words.shape[0]
+            if out is None:
+                out = (np.empty_like(words), np.empty(cnt, np.uint8), np.empty(cnt, np.uint8))
+        corrected, nerr, failed = out
+        self.ctx._check(_lib.lib().ccgpu_gf_decode(self.ctx._h, self._h, _ptr(words), cnt, _ptr(corrected), _ptr(nerr),
+                                                   _ptr(failed)))
+        return corrected, nerr, failed
+
+
+def sigma(rate, ebno_db):
+    return _lib.lib().ccgpu_sigma(float(rate), float(ebno_db))
+
+
+def gf_tables(q, poly=0):
+    size = 1 << q
+    exp = np.zeros(2 * size, np.uint16)
+    log = np.zeros(size, np.uint16)
+    rc = _lib.lib().ccgpu_gf_tables(q, poly, exp.ctypes.data, log.ctypes.data)
+    if rc != 0:
+        raise CcgpuError(rc, "ccgpu_gf_tables")
+    return exp, log

@@ -1,0 +1,193 @@
+/* ccgpu.h -- C ABI of libccgpu.so, the B200 (sm_100a) engine behind the hot path of
+ * hannesweisbach/channelcoding: iterative min-sum-family decoding of binary BCH codes on their
+ * parity-check matrix inside an AWGN Monte-Carlo sweep, plus batched GF(2^q) algebraic BCH/RS
+ * decoding.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * The reference has no FFI: its boundary is C++ duck typing.  Each entry point
+ * below names the reference interface it replaces (paths relative to the reference's src/).
+ * INTEGRATION.md shows the binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative ccgpu_status on error; the text of the
+ *     last error of a context is available from ccgpu_last_error().  Nothing throws.
+ *   - a per-frame decoding failure is DATA (failed[f] = 1), never an error code -- the
+ *     reference's `decoding_failure` exception (codes/codes.h:28-36) is a normal outcome that the
+ *     simulation counts (simulation/simulation.c++:133-135).
+ *   - the caller owns every buffer.  Data pointers may be host or device pointers (detected with
+ *     cudaPointerGetAttributes); host buffers are staged through pinned memory and the call
+ *     returns after the results are in the caller's buffer; with device buffers the work is
+ *     enqueued on the context's stream and the call returns immediately (ccgpu_sync to wait).
+ *   - a context is bound to one CUDA device and one stream and is internally locked, so the
+ *     reference's pool threads (simulation/simulation.c++:240-273) may share it.
+ *   - there is no CPU fallback: without a usable CUDA device ccgpu_create fails.
+ */
+#ifndef CCGPU_H
+#define CCGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCGPU_ABI_VERSION 1
+
+typedef struct ccgpu_ctx ccgpu_ctx;
+typedef struct ccgpu_code ccgpu_code;
+
+typedef enum {
+  CCGPU_OK = 0,
+  CCGPU_ERR_INVALID = -1,     /* bad argument */
+  CCGPU_ERR_CUDA = -2,        /* CUDA runtime error (text in ccgpu_last_error) */
+  CCGPU_ERR_UNSUPPORTED = -3, /* valid request the engine has no kernel for */
+  CCGPU_ERR_NO_DEVICE = -4    /* no CUDA device / extension not usable: there is no CPU fallback */
+} ccgpu_status;
+
+/* ---- decoder variants: the six soft-decision tags of codes/soft_decision.h:20-73 ------------- */
+typedef enum {
+  CCGPU_MS = 0,    /* min_sum_tag                  "MS"    soft_decision.h:20-23, :220-226 */
+  CCGPU_NMS = 1,   /* normalized_min_sum_tag       "NMS"   :36-42, :228-237   r = alpha * min          */
+  CCGPU_OMS = 2,   /* offset_min_sum_tag           "OMS"   :44-50, :239-253   r = max(min - beta, 0) in double */
+  CCGPU_SCMS1 = 3, /* self_correcting_1_min_sum_tag "SCMS1" :52-56, :256-268                           */
+  CCGPU_SCMS2 = 4, /* self_correcting_2_min_sum_tag "SCMS2" :58-62, :270-282                           */
+  CCGPU_NMS2D = 5, /* normalized_2d_min_sum_tag    "2DNMS" :64-73, :284-295   r = alpha*min, q = beta*e + y */
+  CCGPU_SPA = 6    /* sum-product (tanh rule); extension, not in the reference                         */
+} ccgpu_variant;
+
+/* ---- stop rules ------------------------------------------------------------ */
+typedef enum {
+  CCGPU_STOP_REF_ZERO_OVERLAP = 0, /* syndrome(H,b) of soft_decision.h:79-84 as executed: every row's
+                                      integer overlap with b is 0 mod 256 (math/matrix.h:57-67)        */
+  CCGPU_STOP_GF2_PARITY = 1,       /* H b^T = 0 over GF(2): what a syndrome check means               */
+  CCGPU_STOP_NONE = 2              /* run exactly max_iter iterations, never fail (max_iter = 1 gives
+                                      the behaviour of the reference's HEAD, math/matrix.h:50)         */
+} ccgpu_stop_rule;
+
+typedef struct {
+  int32_t variant;    /* ccgpu_variant */
+  int32_t stop_rule;  /* ccgpu_stop_rule */
+  uint32_t max_iter;  /* template parameter Iterations of the reference's tags (50 in benchmark.c++) */
+  uint32_t reserved;
+  double alpha;       /* NMS / 2DNMS scale  (std::ratio parameter of the tag) */
+  double beta;        /* OMS offset / 2DNMS variable-node scale; must be >= 0 for OMS */
+} ccgpu_ms_params;
+
+/* error / iteration counters of one Monte-Carlo batch; all-zero codeword transmitted like
+ * simulation.c++:113-131.  frame_errors is the reference's word_errors. */
+typedef struct {
+  uint64_t frames;
+  uint64_t frame_errors; /* decoding failure OR any decided bit != 0 (simulation.c++:126-135) */
+  uint64_t bit_errors;   /* decided bits != 0, failures included */
+  uint64_t iterations;   /* decoder iterations executed, summed over frames */
+  uint64_t failures;     /* decoding_failure (no stop within max_iter) */
+  uint64_t undetected;   /* stop test passed on a non-zero word (impossible under REF_ZERO_OVERLAP) */
+  uint64_t reserved[2];
+} ccgpu_counters;
+
+typedef struct {
+  uint32_t family;     /* 0 = binary primitive BCH (codes/bch.h), 1 = RS (codes/rs.h), 2 = from dense H */
+  uint32_t q;          /* field GF(2^q) */
+  uint32_t n, l, k;    /* length, information symbols l = n - k, k = deg g (cyclic.h:104-105,273) */
+  uint32_t dmin;       /* consecutive_zeroes(g) + 1 as computed by cyclic.h:186-204 (sic for RS) */
+  uint32_t t;          /* correction_capability (codes.h:15-26) */
+  uint32_t h_rows;     /* rows of the parity-check matrix in use */
+  uint32_t row_weight; /* max row weight */
+  uint32_t edges;      /* ones in H */
+  uint32_t h_kind;     /* 0 = cyclic taps without wrap (cyclic.h:346-359), 1 = cyclic with wrap
+                          (redundant rows), 2 = general (CSR) */
+  uint32_t kernel;     /* 0 = none (algebraic only), 1 = ms_cyclic (lane per row), 2 = ms_csr */
+  double rate;         /* l / n (cyclic.h:274) */
+} ccgpu_code_info;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int ccgpu_abi_version(void);
+/* device: CUDA ordinal.  Replaces nothing in the reference (it has no device). */
+int ccgpu_create(int device, ccgpu_ctx **out);
+void ccgpu_destroy(ccgpu_ctx *ctx);
+const char *ccgpu_last_error(const ccgpu_ctx *ctx);
+/* use an existing cudaStream_t (e.g. torch's current stream) instead of the context's own */
+int ccgpu_set_stream(ccgpu_ctx *ctx, void *cuda_stream);
+void *ccgpu_get_stream(ccgpu_ctx *ctx);
+int ccgpu_sync(ccgpu_ctx *ctx);
+/* number of engine kernels launched through this context so far */
+uint64_t ccgpu_kernel_launches(const ccgpu_ctx *ctx);
+
+/* ---- codes ---------------------------------------------------------------------------------------
+ * cyclic::primitive_bch<q, Capability>() -- codes/bch.h:16-161 on top of codes/cyclic.h:67-386.
+ * cap_kind 0 = errors<cap_value>, 1 = dmin<cap_value> (codes/codes.h:7-26).  Builds g (lcm of the
+ * minimal polynomials of alpha^1, alpha^3, ...), h = (x^n+1)/g, k, l, dmin, rate and the k x n
+ * parity-check matrix H() of cyclic.h:346-359, and uploads it.
+ * For the three constructors ctx may be NULL: the result is then a host-only description
+ * (info / to_string / H / poly / encode work, decoding calls are rejected). */
+int ccgpu_bch_create(ccgpu_ctx *ctx, uint32_t q, int cap_kind, uint32_t cap_value, ccgpu_code **out);
+/* cyclic::rs<q, errors<t>, Sigma, N, Coding, mu, step>() -- codes/rs.h:6-94. */
+int ccgpu_rs_create(ccgpu_ctx *ctx, uint32_t q, uint32_t t, uint32_t mu, uint32_t step, ccgpu_code **out);
+/* any dense 0/1 matrix exactly as matrix<uint8_t> from H<T>() / H_alt<T>() (math/matrix.h:11-70),
+ * row-major rows x cols.  Cyclic-tap structure is detected; anything else runs on the CSR kernel.
+ * rate is used for sigma(Eb/N0) only (simulation.c++:83-85). */
+int ccgpu_code_from_dense(ccgpu_ctx *ctx, const uint8_t *H, uint32_t rows, uint32_t cols, double rate,
+                          ccgpu_code **out);
+/* switch a BCH code to the redundant H with `rows` cyclic shifts of the first row (k <= rows <= n);
+ * extension: the reference only builds the k-row H (generate_n(k - 1), cyclic.h:353-356). */
+int ccgpu_code_set_rows(ccgpu_code *code, uint32_t rows);
+void ccgpu_code_destroy(ccgpu_code *code);
+int ccgpu_code_get_info(const ccgpu_code *code, ccgpu_code_info *out);
+/* "(n, l, dmin)-TAG" -- cyclic::to_string(), cyclic.h:282-287; it is the log-file name
+ * (simulation.c++:98) and parsed by the CLI (benchmark.c++:214-240). */
+int ccgpu_code_to_string(const ccgpu_code *code, const char *tag, char *buf, size_t cap);
+int ccgpu_code_H(const ccgpu_code *code, uint8_t *out /* h_rows x n */);
+/* which: 0 = g(x), 1 = h(x); coefficients low degree first; returns the count or <0 */
+int ccgpu_code_poly(const ccgpu_code *code, int which, uint16_t *out, size_t cap);
+/* exp[2*2^q], log[2^q] of math::ef_element<2,q> (math/galois.h:269-301); poly 0 = default table :18-20 */
+int ccgpu_gf_tables(uint32_t q, uint32_t poly, uint16_t *exp_out, uint16_t *log_out);
+/* cyclic::encode with division_tag (cyclic.h:35-40, :289-311): count x l symbols -> count x n */
+int ccgpu_encode(const ccgpu_code *code, const uint8_t *msgs, uint64_t count, uint8_t *words);
+
+/* ---- decoding ----------------------------------------------------------------------------------
+ * min_sum<float,uint8_t>(H, y, Tag{}) for `frames` frames -- codes/soft_decision.h:161-202,
+ * :220-295, as reached from cyclic::correct_(.., soft_decision_tag) (cyclic.h:254-267) and
+ * decoder::correct (simulation/simulation.h:62-65).
+ *   y      frames x n   channel values, raw (the reference does not scale to LLRs)
+ *   bits   frames x n   hard decision b of the last executed iteration (codes.h:43-52), 0/1
+ *   L      frames x n   totals L of that iteration (soft_decision.h:180-182); nullable
+ *   iter   frames       0-based iteration index at which the stop test passed
+ *                       (std::get<2> of the reference's tuple); max_iter on failure; nullable
+ *   failed frames       1 where the reference throws decoding_failure (soft_decision.h:201) */
+int ccgpu_decode_llr(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, const float *y,
+                     uint64_t frames, uint8_t *bits, float *L, uint8_t *iter, uint8_t *failed);
+
+/* sigma of simulation.c++:83-85: 1 / sqrt(2 * rate * 10^(ebno_db/10)) */
+double ccgpu_sigma(double rate, double ebno_db);
+
+/* channel only: y[f][c] = 1 + sigma * z, z ~ N(0,1) from Philox4x32-10 keyed (seed, point),
+ * counter (frame0 + f, c / 4)  -- replaces std::generate(b, noise) of simulation.c++:113-115, :125 */
+int ccgpu_awgn_llr(ccgpu_ctx *ctx, uint32_t n, double sigma, uint64_t seed, uint32_t point, uint64_t frame0,
+                   uint64_t frames, float *y);
+
+/* one Eb/N0 point of awgn_simulation::operator() (simulation.c++:112-149) for global frames
+ * [frame0, frame0 + frames): channel + decode + error test fused on chip; only counters leave
+ * the GPU.  `out` may be a host or device pointer (device: accumulated into, caller zeroes). */
+int ccgpu_awgn_point(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, double ebno_db,
+                     uint64_t seed, uint32_t point, uint64_t frame0, uint64_t frames, ccgpu_counters *out);
+
+/* one weight class of bitflip_simulation::operator() (simulation.c++:156-213): all C(n, weight)
+ * inputs x = -2*bit + 1, decoded and counted; patterns [first, first + count) in the
+ * lexicographic order of std::next_permutation (count 0 = all). */
+int ccgpu_bitflip_point(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, uint32_t weight,
+                        uint64_t first, uint64_t count, ccgpu_counters *out);
+
+/* cyclic::correct_(.., hard_decision_tag) -- cyclic.h:207-252: syndromes (cyclic.h:53-63), error
+ * locator (codes/hard_decision.h:61-196; the engine runs Berlekamp-Massey, which computes the same
+ * bounded-distance result as the reference's PGZ/BM/Euklid tags), roots (cyclic.h:126-150), error
+ * values (bch.h:80-83 / rs.h:41-78), correction and the re-syndrome check (cyclic.h:237-248).
+ *   words     count x n  symbols (uint8)     corrected count x n (received word where failed)
+ *   n_errors  count      number of corrected symbols (cyclic.h:237); nullable
+ *   failed    count      1 where the reference throws decoding_failure */
+int ccgpu_gf_decode(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8_t *words, uint64_t count,
+                    uint8_t *corrected, uint8_t *n_errors, uint8_t *failed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CCGPU_H */

@@ -1,0 +1,82 @@
+"""CPU-only checks of the product's host side: libccgpu.so loads and exports every symbol that
+include/ccgpu.h declares, and the host logic behind the ABI (code construction, GF tables, encoding,
+sigma, to_string) reproduces the reference's values from tests/golden/.  No kernel is launched."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import channelcoding_b200 as cc
+from channelcoding_b200 import _lib
+from conftest import ROOT, golden_H, load_golden
+
+
+def test_header_symbols_exported():
+    with open(os.path.join(ROOT, "include", "ccgpu.h")) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    declared = set(re.findall(r"\b(ccgpu_[A-Za-z_0-9]+)\s*\(", text))
+    assert declared == set(_lib.EXPORTS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.ccgpu_abi_version() == 1
+
+
+def test_no_device_is_loud():
+    """no CUDA device here: creating a context must fail, there is no CPU fallback"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(cc.CcgpuError):
+        cc.Context(0)
+
+
+@pytest.mark.parametrize("q", range(1, 9))
+def test_gf_tables(q, golden_codes):
+    exp, log = cc.gf_tables(q)
+    assert np.array_equal(exp, golden_codes["gf%d.exp" % q])
+    assert np.array_equal(log, golden_codes["gf%d.log" % q])
+
+
+def test_code_construction(catalogue, golden_codes):
+    for name, e in catalogue.items():
+        if e["family"] == 0:
+            c = cc.host_bch(e["q"], **({"errors": e["cap_value"]} if e["cap_kind"] == 0 else {"dmin": e["cap_value"]}))
+        else:
+            c = cc.host_rs(e["q"], e["t"])
+        assert (c.n, c.l, c.k, c.dmin, c.t) == (e["n"], e["l"], e["k"], e["dmin"], e["t"]), name
+        assert c.rate == e["rate"]
+        assert np.array_equal(c.poly("g"), golden_codes[name + ".g"])
+        assert np.array_equal(c.poly("h"), golden_codes[name + ".h"])
+        for tag, s in e["to_string"].items():
+            assert c.to_string(tag) == s
+        if e["family"] == 0:
+            assert np.array_equal(c.H(), golden_H(golden_codes, catalogue, name))
+            assert c.h_kind == 0 and c.edges == c.h_rows * c.row_weight
+            c.set_rows(c.n)  # redundant H: n cyclic shifts, wraps
+            assert c.h_kind == 1 and c.h_rows == c.n
+            assert np.array_equal(c.H()[: e["k"]], golden_H(golden_codes, catalogue, name))
+
+
+def test_h_alt_is_general(catalogue, golden_codes):
+    """the reference's H_alt (cyclic.h:361-385) is not cyclic: the engine classifies it for the CSR kernel"""
+    Halt = golden_H(golden_codes, catalogue, "bch_63_45", alt=True)
+    c = cc.host_from_dense(Halt, 45 / 63)
+    assert c.h_kind == 2 and c.n == 63 and c.h_rows == Halt.shape[0]
+
+
+@pytest.mark.parametrize("name", ["rs_255_223", "rs_15_9", "rs_7_3", "bch_63_36", "bch_255_131"])
+def test_encode(name, catalogue):
+    g = load_golden("hard_%s.npz" % name)
+    e = catalogue[name]
+    c = cc.host_bch(e["q"], errors=e["t"]) if e["family"] == 0 else cc.host_rs(e["q"], e["t"])
+    assert np.array_equal(c.encode(g["msgs"]), g["words"])
+
+
+def test_sigma():
+    import oracle
+    for rate, eb in ((36 / 63, 4.0), (7 / 15, 1.0), (131 / 255, 8.0)):
+        assert cc.sigma(rate, eb) == oracle.sigma(rate, eb)
