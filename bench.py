@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json): decoded frames/s and info-bits/s,
+BCH(63,36) normalised min-sum (alpha = 0.8, <= 50 iterations, early exit), 1/2/4/8 B200 vs host CPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--ebno 4.0]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step is one pass of the hot path over one batch of synthetic AWGN frames (all-zero codeword, like
+the reference's simulation).  Three measurements per run:
+  value   frames/s of ccgpu_decode_llr with the LLR batch resident in HBM (device pointers), CUDA
+          events on the launching stream, max over ranks.  The batch (1.06 GB) is far larger than L2.
+  e2e     the same call through the C ABI with HOST buffers: pinned y in, bits/iter/failed out,
+          H2D + decode + D2H inside the timed region.
+  fused   ccgpu_awgn_point (the Monte-Carlo product path: Philox channel + decode + counters fused,
+          only 64 bytes leave the GPU), followed by the one NCCL all-reduce of the counters.
+The CPU baseline is the reference's own decoder (oracle/_ref/libccref.so = the reference compiled by
+oracle/build_ref.sh) running simulation.c++'s inner loop on all host cores; if that library is absent,
+the C restatement in oracle/ (kind "port").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+Q, T, ALPHA, MAX_ITER = 6, 5, 0.8, 50
+N, L_INFO, ROWS, W = 63, 36, 27, 18
+EDGES = ROWS * W
+ALGO_BYTES_PER_FRAME = 4 * N + 4 * ((N + 31) // 32) + 4  # LLR in, packed decisions + status out
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "measured"
+    except Exception:
+        return 6650.0, 1965.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)"""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == "Active" for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference(ebno, seconds, frames_per_thread=0):
+    """the reference's CPU decoder on all host cores -> (frames/s, cores, kind, word_errors, frames)"""
+    cores = os.cpu_count() or 1
+    import ccref
+    if ccref.available():
+        ref = ccref.Ref()
+        frames, werr, el = ref.awgn_baseline(ccref.FAM_BCH, Q, ccref.CAP_ERRORS, T, ccref.ALG_SOFT0 + ccref.V_NMS, ebno,
+                                             seed=0, seconds=seconds, threads=cores,
+                                             max_frames_per_thread=frames_per_thread)
+        return frames / el, cores, "reference", werr, frames
+    # port: the C restatement, one python thread per core (ctypes releases the GIL)
+    import numpy as np
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+    code = oracle.Code(0, Q, T)
+    H = code.H()
+    sig = oracle.sigma(code.rate, ebno)
+    per = frames_per_thread or 200
+
+    def work(t):
+        rng = np.random.default_rng(t)
+        done = err = 0
+        t0 = time.time()
+        while True:
+            y = (1 + sig * rng.standard_normal((per, N))).astype(np.float32)
+            bits, _, _, failed = oracle.min_sum(H, y, "NMS", ALPHA, 0.0, MAX_ITER)
+            done += per
+            err += int(((failed == 1) | bits.any(axis=1)).sum())
+            if frames_per_thread or time.time() - t0 >= seconds:
+                return done, err
+    t0 = time.time()
+    with ThreadPoolExecutor(cores) as ex:
+        res = list(ex.map(work, range(cores)))
+    el = time.time() - t0
+    frames = sum(r[0] for r in res)
+    return frames / el, cores, "port", sum(r[1] for r in res), frames
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_thread = 300  # frames per thread per step: a bounded sample of the workload
+    for _ in range(args.warmup):
+        cpu_reference(args.ebno, 1e9, per_thread)
+    t0 = time.time()
+    frames = werr = 0
+    for _ in range(args.steps):
+        rate, cores, kind, e, f = cpu_reference(args.ebno, 1e9, per_thread)
+        frames += f
+        werr += e
+    el = time.time() - t0
+    value = frames / el
+    line = {
+        "impl": "reference", "metric": "decoded frames/s, BCH(63,36) normalised min-sum", "value": value,
+        "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BCH(63,36) t=5 NMS alpha=0.8, <=50 iterations, reference stop rule, AWGN Eb/N0=%g dB, "
+                               "all-zero codeword" % args.ebno, "ebno_db": args.ebno,
+                   "frames_per_step": frames // max(1, args.steps)},
+        "info_bits_per_s": value * L_INFO, "wer": werr / max(1, frames),
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
+                         "sample": "%d frames per thread per step, %d threads, simulation.c++ inner loop incl. noise "
+                                   "generation" % (per_thread, cores)},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--ebno", type=float, default=4.0)
+    ap.add_argument("--frames", type=int, default=1 << 22, help="frames per step per GPU (resident batch)")
+    ap.add_argument("--e2e-frames", type=int, default=1 << 20, help="frames per step per GPU for the host-buffer path")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import channelcoding_b200 as cc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = cc.Context(local)
+    ctx.use_torch_stream()
+    code = ctx.bch(Q, errors=T)
+    assert (code.n, code.l, code.h_rows, code.row_weight, code.kernel) == (N, L_INFO, ROWS, W, 1)
+    B = args.frames
+    sig = cc.sigma(code.rate, args.ebno)
+    dev = torch.device("cuda", local)
+    y = torch.empty((B, N), dtype=torch.float32, device=dev)
+    ctx.awgn_llr(N, np.float32(sig), seed=0, point=int(round(args.ebno * 2)), frame0=rank * B, frames=B, out=y)
+    out = (torch.empty((B, N), dtype=torch.uint8, device=dev), None, torch.empty(B, dtype=torch.uint8, device=dev),
+           torch.empty(B, dtype=torch.uint8, device=dev))
+
+    def step_resident():
+        code.decode(y, "NMS", ALPHA, 0.0, MAX_ITER, out=out, want_L=False)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            fn()
+        ev1.record()
+        barrier()
+        ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches
+    ms_res = timed(step_resident, args.steps, args.warmup)
+    launches = ctx.kernel_launches - launches0 - args.warmup
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * args.steps / (ms_res * 1e-3)
+
+    # iteration statistics of the batch (for the ALU model and the log)
+    it = out[2].to(torch.int64)
+    failed = out[3].to(torch.int64)
+    iters_exec = torch.where(failed == 1, torch.full_like(it, MAX_ITER), it + 1).double().mean().item()
+    wer = ((failed == 1) | (out[0].sum(dim=1) > 0)).double().mean().item()
+
+    # ---- e2e: host buffers through the C ABI
+    Be = args.e2e_frames
+    y_host = torch.empty((Be, N), dtype=torch.float32).pin_memory()
+    y_host.copy_(y[:Be])
+    h_bits = torch.empty((Be, N), dtype=torch.uint8).pin_memory()
+    h_it = torch.empty(Be, dtype=torch.uint8).pin_memory()
+    h_fail = torch.empty(Be, dtype=torch.uint8).pin_memory()
+    e2e_out = (h_bits.numpy(), None, h_it.numpy(), h_fail.numpy())
+    y_np = y_host.numpy()
+
+    def step_e2e():
+        code.decode(y_np, "NMS", ALPHA, 0.0, MAX_ITER, out=e2e_out, want_L=False)
+
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()  # returns after the results are in the host buffers
+    torch.cuda.synchronize()
+    el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    e2e_value = world * Be * e2e_steps / float(el.item())
+    assert np.array_equal(h_fail.numpy(), out[3][:Be].cpu().numpy())
+
+    # ---- fused Monte-Carlo point + the one all-reduce of the counters
+    counters = torch.zeros(8, dtype=torch.int64, device=dev)
+    point = int(round(args.ebno * 2))
+    state = {"step": 0}
+
+    def step_fused():
+        f0 = (state["step"] * world + rank) * B
+        code.awgn_point(args.ebno, B, "NMS", ALPHA, 0.0, MAX_ITER, seed=0, point=point, frame0=f0, out=counters)
+        state["step"] += 1
+
+    ms_fused = timed(step_fused, args.steps, args.warmup)
+    if world > 1:
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)  # frames sharded, counters merged once per point
+    cnt = counters.cpu().numpy()
+    fused_value = world * B * args.steps / (ms_fused * 1e-3)
+
+    if rank == 0:
+        hbm_peak, sm_max, which = measured_peaks()
+        kernel_ms = ms_res / args.steps
+        achieved = B * ALGO_BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
+        lane_ops = iters_exec * (11 * EDGES + 2 * N)
+        alu_peak = 148 * 128 * sm_max * 1e6
+        line = {
+            "metric": "decoded frames/s, BCH(63,36) normalised min-sum", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "BCH(63,36) t=5 NMS alpha=0.8, <=50 iterations, reference stop rule, AWGN "
+                                   "Eb/N0=%g dB, all-zero codeword, %d frames per step per GPU resident in HBM "
+                                   "(%.2f GB of LLRs, larger than L2)" % (args.ebno, B, B * N * 4 / 1e9),
+                       "ebno_db": args.ebno, "frames_per_step_per_gpu": B, "l2": "inputs larger than L2",
+                       "sharding": "frames split across ranks, no data-path collective"},
+            "info_bits_per_s": value * L_INFO, "wer": wer, "avg_iterations": iters_exec,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": Be * N * 4,
+                    "d2h_bytes_per_step": Be * (N + 2), "frames_per_step_per_gpu": Be,
+                    "path": "ccgpu_decode_llr with pinned host buffers"},
+            "fused_monte_carlo": {"value": fused_value, "unit": "frames/s", "ms_per_step": ms_fused / args.steps,
+                                  "wer": float(cnt[1]) / max(1, int(cnt[0])),
+                                  "avg_iterations": float(cnt[3]) / max(1, int(cnt[0])), "frames": int(cnt[0]),
+                                  "path": "ccgpu_awgn_point (Philox channel + decode + counters on chip) + one NCCL "
+                                          "all-reduce of 8 counters"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": which,
+                         "kernel": "ms_cyclic_kernel<W=18,RPL=1,NP=2,SC=0,WRAP=0>",
+                         "bytes_per_frame": ALGO_BYTES_PER_FRAME,
+                         "note": "the decoder is on-chip ALU/shared-memory bound, not HBM bound: see alu"},
+            "alu": {"model": "avg_iters*(11E+2n) lane-ops/frame (SURVEY 8d)", "lane_ops_per_frame": lane_ops,
+                    "achieved_lane_ops_per_s": value / world * lane_ops, "peak_lane_ops_per_s": alu_peak,
+                    "frac": value / world * lane_ops / alu_peak},
+            "clocks": clocks,
+        }
+        if not args.no_cpu:
+            rate, cores, kind, werr, frames = cpu_reference(args.ebno, args.cpu_seconds)
+            line["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": cores, "kind": kind,
+                                    "sample": "%.0f s wall on %d threads = %d frames of the same workload "
+                                              "(simulation.c++ inner loop incl. noise generation), WER %.4f"
+                                              % (args.cpu_seconds, cores, frames, werr / max(1, frames))}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

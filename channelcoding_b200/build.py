@@ -4,7 +4,7 @@
 
 nvcc cross-compiles without a GPU.  Objects go to channelcoding_b200/csrc/_obj/, the library to
 channelcoding_b200/libccgpu.so (git-ignored, shipped to the GPU box by gpurun).  The min-sum kernel
-instantiation groups (csrc/ms_cyclic_list.h) are compiled in parallel.
+instantiation groups (csrc/ms_shapes_generated.h) are compiled in parallel.
 """
 import concurrent.futures
 import os
@@ -22,7 +22,7 @@ FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", 
 
 
 def _groups():
-    with open(os.path.join(CSRC, "ms_cyclic_list.h")) as f:
+    with open(os.path.join(CSRC, "ms_shapes_generated.h")) as f:
         return int(re.search(r"#define CCGPU_MS_GROUPS (\d+)", f.read()).group(1))
 
 

@@ -31,6 +31,7 @@ struct ccgpu_ctx {
   void *d_stage = nullptr;
   size_t d_stage_bytes = 0;
   unsigned long long *d_counters = nullptr;
+  unsigned long long *d_work = nullptr;  // queue head of the dynamically scheduled kernels
   ccgpu_counters *h_counters = nullptr;  // pinned
 };
 
@@ -38,11 +39,10 @@ struct ccgpu_code {
   ccgpu_ctx *ctx = nullptr;
   CodeSpec spec;
   HShape shape;
-  // min-sum kernel selection for SC = 0 / 1
-  const MsCyclicEntry *cyc[2] = { nullptr, nullptr };
-  int fpw[2] = { 1, 1 };
-  int grid_max[2] = { 0, 0 };
-  size_t smem[2] = { 0, 0 };
+  // min-sum kernel selection per vertical-node flavour (VN_PLAIN, VN_SC, VN_2D)
+  const MsCyclicEntry *cyc[3] = { nullptr, nullptr, nullptr };
+  int grid_max[3] = { 0, 0, 0 };
+  size_t smem[3] = { 0, 0, 0 };
   MsCsrDevice csr;     // general-H kernel tables (device)
   GfDevice gf;         // algebraic decoder tables (device)
 };
@@ -115,36 +115,30 @@ __global__ void __launch_bounds__(kAwgnThreads) awgn_llr_kernel(float *__restric
   }
 }
 
-// pick the cyclic kernel instantiation for this H (nullptr: none fits -> CSR kernel)
+// pick the cyclic kernel instantiations (one per vertical-node flavour) compiled for exactly this
+// H: same n, same tap offsets, and either the same number of rows without wrap-around or a
+// redundant (run-time rows, wrap-around) shape.  Nothing fits -> CSR kernel.
 void select_cyclic(ccgpu_code *c) {
-  for (int sc = 0; sc < 2; ++sc) c->cyc[sc] = nullptr;
+  for (int vn = 0; vn < 3; ++vn) c->cyc[vn] = nullptr;
   if (c->shape.kind > 1 || c->shape.taps.empty()) return;
   const int n = static_cast<int>(c->spec.n), k = static_cast<int>(c->spec.rows);
   const int w = static_cast<int>(c->shape.taps.size());
-  const int wrap = c->shape.kind;
-  if (w > kMaxTaps) return;
-  for (int sc = 0; sc < 2; ++sc) {
-    long best_score = -1;
-    for (int i = 0, m = ms_cyclic_count(); i < m; ++i) {
-      const MsCyclicEntry *e = ms_cyclic_at(i);
-      if (e->w != w || e->sc != sc || e->wrap < wrap || e->rpl * 32 < k || 32 * e->np < n) continue;
-      int fpw = 1;
-      if (e->rpl == 1) fpw = std::max(1, std::min({ 32 / k, 4, (32 * e->np) / n }));
-      // prefer: exact wrap, fewer rows per lane, more frames per warp, fewer passes
-      const long score = (e->wrap == wrap ? 1000000 : 0) + (8 - e->rpl) * 10000 + fpw * 100 + (16 - e->np);
-      if (score > best_score) {
-        best_score = score;
-        c->cyc[sc] = e;
-        c->fpw[sc] = fpw;
-      }
-    }
-    if (c->cyc[sc]) {
-      c->smem[sc] = size_t(kMsThreads / 32) * 2 * 32 * c->cyc[sc]->np * sizeof(float);
-      int occ = 0;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void *>(c->cyc[sc]->fn),
-                                                    kMsThreads, c->smem[sc]);
-      c->grid_max[sc] = std::max(1, occ) * c->ctx->sm_count;
-    }
+  for (int i = 0, m = ms_cyclic_count(); i < m; ++i) {
+    const MsCyclicEntry *e = ms_cyclic_at(i);
+    if (e->n != n || e->w != w || !std::equal(c->shape.taps.begin(), c->shape.taps.end(), e->taps)) continue;
+    const bool exact = e->k == k && !e->wrap && c->shape.kind == 0;
+    const bool redundant = e->k == 0 && e->wrap && k <= 32 * e->rpl;
+    if (!exact && !redundant) continue;
+    if (c->cyc[e->vn] && !exact) continue;  // an exact shape wins over the redundant one
+    c->cyc[e->vn] = e;
+  }
+  for (int vn = 0; vn < 3; ++vn) {
+    if (!c->cyc[vn]) continue;
+    c->smem[vn] = size_t(kMsThreads / 32) * 2 * 32 * c->cyc[vn]->np * sizeof(float);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void *>(c->cyc[vn]->fn), kMsThreads,
+                                                  c->smem[vn]);
+    c->grid_max[vn] = std::max(1, occ) * c->ctx->sm_count;
   }
 }
 
@@ -186,17 +180,16 @@ void fill_decoder(MsParams &mp, const ccgpu_code *c, const ccgpu_ms_params *p) {
 // launch the min-sum decoder for one batch described by mp (source/outputs already filled)
 int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsParams mp) {
   if (mp.frames == 0) return CCGPU_OK;
-  const int sc = (p->variant == CCGPU_SCMS1 || p->variant == CCGPU_SCMS2) ? 1 : 0;
-  if (p->variant != CCGPU_SPA && c->cyc[sc]) {
-    const MsCyclicEntry *e = c->cyc[sc];
-    mp.w = e->w;
-    mp.fpw = c->fpw[sc];
-    for (int j = 0; j < e->w; ++j) mp.tap[j] = static_cast<int16_t>(c->shape.taps[j]);
-    const uint64_t per_cta = uint64_t(kMsThreads / 32) * mp.fpw;
+  const int vn = (p->variant == CCGPU_SCMS1 || p->variant == CCGPU_SCMS2) ? VN_SC : (p->variant == CCGPU_NMS2D ? VN_2D : VN_PLAIN);
+  if (p->variant != CCGPU_SPA && c->cyc[vn]) {
+    const MsCyclicEntry *e = c->cyc[vn];
+    const uint64_t per_cta = uint64_t(kMsThreads / 32) * e->fpw;
     const uint64_t want = (mp.frames + per_cta - 1) / per_cta;
-    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(want, c->grid_max[sc]));
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(want, c->grid_max[vn]));
+    CU(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned long long), ctx->stream));
+    mp.work = ctx->d_work;
     void *args[] = { &mp };
-    CU(cudaLaunchKernel(reinterpret_cast<const void *>(e->fn), dim3(grid), dim3(kMsThreads), args, c->smem[sc],
+    CU(cudaLaunchKernel(reinterpret_cast<const void *>(e->fn), dim3(grid), dim3(kMsThreads), args, c->smem[vn],
                         ctx->stream));
     ctx->launches++;
     return CCGPU_OK;
@@ -228,6 +221,7 @@ int ccgpu_create(int device, ccgpu_ctx **out) {
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
       cudaMalloc(&ctx->d_counters, sizeof(ccgpu_counters)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_work, sizeof(unsigned long long)) != cudaSuccess ||
       cudaMallocHost(&ctx->h_counters, sizeof(ccgpu_counters)) != cudaSuccess) {
     cudaGetLastError();
     delete ctx;
@@ -243,6 +237,7 @@ void ccgpu_destroy(ccgpu_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->d_work) cudaFree(ctx->d_work);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;

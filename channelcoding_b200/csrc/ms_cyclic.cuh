@@ -6,8 +6,9 @@
 //
 // Mapping (one warp owns FPW frames; nothing but the final decisions/counters leaves the SM):
 //   * lane <-> parity-check ROW.  The row's W edge messages r[j] live in REGISTERS for the whole
-//     decode (W is a template parameter, loops fully unrolled, tap offsets come from the
-//     __grid_constant__ parameter block = constant bank operands).
+//     decode.  The shape of H (ms_shape.h: n, rows, tap offsets, rows per lane, frames per warp) is
+//     a template parameter: every loop is fully unrolled and every shared-memory access is
+//     [per-lane base register + immediate], so an edge costs no address arithmetic.
 //   * per frame only y[n] and the column sums S[n] live in shared memory (2n floats).
 //   * VN+CN pass: q_j = (S[c_j] - r_j) + y[c_j] exactly as soft_decision.h:135-136; min1/min2 and
 //     the sign parity are reduced IN the lane (a row is private to a lane: no shuffles), then
@@ -20,7 +21,9 @@
 //     masks, every row-lane popcounts its row mask against it (integer overlap mod 256 for the
 //     reference's rule, parity for GF(2)).
 //   * frames finish after different iteration counts: every frame group of a warp carries its own
-//     iteration counter and refills itself from a grid-strided frame sequence (persistent warps).
+//     iteration counter and pulls its next frame from a global queue head (atomicAdd) when done,
+//     so no warp idles while others still iterate (persistent warps, dynamic schedule; results do
+//     not depend on the schedule because the noise is keyed by the frame index).
 //
 // Float semantics: additions/multiplications are the explicit _rn intrinsics
 // so nothing is contracted into FMAs; the OMS offset is applied in double; signum(0) = 0 is
@@ -32,6 +35,7 @@
 
 #include "channel.cuh"
 #include "ms_params.h"
+#include "ms_shape.h"
 
 namespace ccgpu {
 
@@ -51,8 +55,6 @@ __device__ __forceinline__ float cn_magnitude(const MsParams &p, float m) {
   return m;
 }
 
-// lexicographic unranking of the `rank`-th length-n 0/1 sequence with `w` ones in the order of
-// std::next_permutation starting from 0..01..1 (simulation.c++:181-199); returns bit of column c
 __device__ __forceinline__ unsigned long long binom(unsigned n, unsigned r) {
   if (r > n) return 0ull;
   unsigned long long v = 1ull;
@@ -60,24 +62,28 @@ __device__ __forceinline__ unsigned long long binom(unsigned n, unsigned r) {
   return v;
 }
 
-template <int W, int RPL, int NP, bool SC, bool WRAP>
+template <class S, int VN>
 __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_constant__ MsParams p) {
+  constexpr int N = S::N, W = S::W, RPL = S::RPL, NP = S::NP, FPW = S::FPW;
+  constexpr bool WRAP = S::WRAP, SC = VN == VN_SC;
+  constexpr int ITEMS = FPW * N;            // columns handled by this warp, <= 32 * NP
+  constexpr int SOFF = 32 * NP;             // S lives SOFF floats after y
+  using T = typename S::taps;
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31;
   const int warp_in_cta = threadIdx.x >> 5;
-  const int n = p.n, k = p.k, fpw = p.fpw;
-  const int items = fpw * n;  // <= 32 * NP columns handled by this warp
-  float *ybuf = smem + warp_in_cta * (2 * 32 * NP);
-  float *sbuf = ybuf + 32 * NP;
+  const int k = S::K > 0 ? S::K : p.k;      // rows (run time only for the redundant shapes)
+  float *const ybuf = smem + warp_in_cta * (2 * SOFF);
+  float *const sbuf = ybuf + SOFF;
 
   // ---------------- row-lane mapping
   int grp = 0;
   int row[RPL];
   bool rvalid[RPL];
   if (RPL == 1) {
-    grp = lane / k;
+    grp = (FPW > 1) ? lane / k : 0;
     row[0] = lane - grp * k;
-    rvalid[0] = grp < fpw;
+    rvalid[0] = (FPW > 1) ? grp < FPW : lane < k;
     if (!rvalid[0]) grp = 0;  // idle lanes shadow group 0's control flow, touch nothing
   } else {
 #pragma unroll
@@ -86,10 +92,17 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
       rvalid[i] = row[i] < k;
     }
   }
-  const int colbase = grp * n;
-  const int lead_lane = (RPL == 1) ? grp * k : 0;  // lane that speaks for the group
+#pragma unroll
+  for (int i = 0; i < RPL; ++i)
+    if (!rvalid[i]) row[i] = 0;  // idle lanes compute on row 0's addresses and store nothing
+  const int colbase = grp * N;
+  const int lead_lane = grp * k;  // lane that speaks for the group (0 when FPW == 1)
   const bool is_lead = (lane == lead_lane) && rvalid[0];
-  const unsigned gmask = (RPL == 1) ? ((k >= 32 ? kFull : ((1u << k) - 1u)) << lead_lane) : kFull;
+  const unsigned gmask = (FPW > 1) ? (((1u << k) - 1u) << lead_lane) : kFull;
+  // per-lane base pointers: edge (row, tap) is yrow[tap] / yrow[SOFF + tap]
+  float *yrow[RPL];
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) yrow[i] = ybuf + colbase + row[i];
 
   // ---------------- column-lane mapping: item c = lane + 32*pass  ->  (frame group, column)
   int cgrp_lead[NP];   // lead lane of the group that owns item c
@@ -99,12 +112,11 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
 #pragma unroll
   for (int ps = 0; ps < NP; ++ps) {
     const int c = lane + 32 * ps;
-    cvalid[ps] = c < items;
-    const int f = (RPL == 1 && cvalid[ps]) ? c / n : 0;
-    ccol[ps] = c - f * n;
-    cgrp_lead[ps] = (RPL == 1) ? f * k : 0;
-    // my group's columns occupy [colbase, colbase + n) of the concatenated word
-    const int lo = colbase - 32 * ps, hi = colbase + n - 32 * ps;
+    cvalid[ps] = c < ITEMS;
+    const int f = (FPW > 1 && cvalid[ps]) ? c / N : 0;
+    ccol[ps] = c - f * N;
+    cgrp_lead[ps] = f * k;
+    const int lo = colbase - 32 * ps, hi = colbase + N - 32 * ps;
     unsigned m = 0;
     if (hi > 0 && lo < 32) {
       const int a = lo < 0 ? 0 : lo, b = hi > 32 ? 32 : hi;
@@ -121,8 +133,8 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
     for (int ps = 0; ps < NP; ++ps) rmask[i][ps] = 0;
 #pragma unroll
     for (int j = 0; j < W; ++j) {
-      int c = row[i] + p.tap[j];
-      if (WRAP && c >= n) c -= n;
+      int c = row[i] + T::get(j);
+      if (WRAP && c >= N) c -= N;
       c += colbase;
 #pragma unroll
       for (int ps = 0; ps < NP; ++ps)
@@ -131,18 +143,15 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
   }
 
   // ---------------- per-group decode state (replicated in every lane of the group)
-  const long long warps_total = static_cast<long long>(gridDim.x) * (kMsThreads / 32);
-  const long long units = warps_total * fpw;
-  long long my_frame = (static_cast<long long>(blockIdx.x) * (kMsThreads / 32) + warp_in_cta) * fpw + grp;
+  const long long units = static_cast<long long>(gridDim.x) * (kMsThreads / 32) * FPW;
+  long long my_frame = (static_cast<long long>(blockIdx.x) * (kMsThreads / 32) + warp_in_cta) * FPW + grp;
   bool active = my_frame < static_cast<long long>(p.frames);
   bool need_init = true;
   int it = 0;
   float r[RPL][W];
   float qold[SC ? RPL : 1][SC ? W : 1];
   unsigned long long cnt_frames = 0, cnt_ferr = 0, cnt_berr = 0, cnt_iter = 0, cnt_fail = 0, cnt_und = 0;
-
-  const bool is2d = p.variant == V_NMS2D;
-  const int nblk = (n + 3) >> 2;
+  constexpr int NBLK = (N + 3) >> 2;
 
   while (true) {
     if (__ballot_sync(kFull, active) == 0u) break;
@@ -155,25 +164,26 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
         for (int ps = 0; ps < NP; ++ps) {
           const long long fr = __shfl_sync(kFull, my_frame, cgrp_lead[ps]);
           if (cvalid[ps] && ((initm >> cgrp_lead[ps]) & 1u)) {
-            ybuf[lane + 32 * ps] = __ldg(p.y + fr * n + ccol[ps]);
+            ybuf[lane + 32 * ps] = __ldg(p.y + fr * N + ccol[ps]);
             sbuf[lane + 32 * ps] = 0.0f;
           }
         }
       } else if (p.src == SRC_PHILOX) {
-        for (int b0 = 0; b0 < fpw * nblk; b0 += 32) {
+#pragma unroll
+        for (int b0 = 0; b0 < FPW * NBLK; b0 += 32) {
           const int b = b0 + lane;
-          const bool bv = b < fpw * nblk;
-          const int f = (RPL == 1 && bv) ? b / nblk : 0;
-          const int blk = b - f * nblk;
-          const int src_lane = (RPL == 1) ? f * k : 0;
+          const bool bv = b < FPW * NBLK;
+          const int f = (FPW > 1 && bv) ? b / NBLK : 0;
+          const int blk = b - f * NBLK;
+          const int src_lane = f * k;
           const long long fr = __shfl_sync(kFull, my_frame, src_lane);
           if (bv && ((initm >> src_lane) & 1u)) {
             const float4 v = awgn_block(p.seed, p.point, p.frame0 + static_cast<uint64_t>(fr), blk, p.sigma);
-            const int c0 = f * n + 4 * blk;
+            const int c0 = f * N + 4 * blk;
             const float vv[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-              if (4 * blk + e < n) {
+              if (4 * blk + e < N) {
                 ybuf[c0 + e] = vv[e];
                 sbuf[c0 + e] = 0.0f;
               }
@@ -183,8 +193,8 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
         if (is_lead && active && need_init) {
           unsigned long long rank = p.frame0 + static_cast<unsigned long long>(my_frame);
           unsigned ones = p.flip_weight;
-          for (int c = 0; c < n; ++c) {
-            const unsigned long long zero_first = binom(n - c - 1, ones);
+          for (int c = 0; c < N; ++c) {
+            const unsigned long long zero_first = binom(N - c - 1, ones);
             float v = 1.0f;
             if (rank >= zero_first && ones > 0) {
               rank -= zero_first;
@@ -216,34 +226,31 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
     for (int i = 0; i < RPL; ++i) {
       float m1 = FLT_MAX, m2 = FLT_MAX;
       unsigned par = 0;
-      if (rvalid[i]) {
 #pragma unroll
-        for (int j = 0; j < W; ++j) {
-          int c = row[i] + p.tap[j];
-          if (WRAP && c >= n) c -= n;
-          c += colbase;
-          const float s = sbuf[c];
-          const float yy = ybuf[c];
-          float e = __fsub_rn(s, r[i][j]);        // exclusive column sum (:135)
-          if (is2d) e = __fmul_rn(p.beta_f, e);   // normalised_vertical (:215-218)
-          float q = __fadd_rn(e, yy);             // unmodified_vertical (:205-209)
-          if (SC) {
-            const float qo = qold[i][j];
-            if (p.variant == V_SCMS1) {            // :261-267
-              const bool keep = (qo == 0.0f) || ((qo > 0.0f) == (q > 0.0f) && (qo < 0.0f) == (q < 0.0f));
-              q = keep ? q : 0.0f;
-            } else {                               // SCMS2 :275-281
-              q = (__fmul_rn(q, qo) > 0.0f) ? q : __fmul_rn(0.5f, __fadd_rn(q, qo));
-            }
-            qold[i][j] = q;
-          } else {
-            r[i][j] = q;  // r_j is dead once q_j exists; reuse its register
+      for (int j = 0; j < W; ++j) {
+        int off = T::get(j);
+        if (WRAP && row[i] + off >= N) off -= N;
+        const float s = yrow[i][SOFF + off];
+        const float yy = yrow[i][off];
+        float e = __fsub_rn(s, r[i][j]);                      // exclusive column sum (:135)
+        if (VN == VN_2D) e = __fmul_rn(p.beta_f, e);          // normalised_vertical (:215-218)
+        float q = __fadd_rn(e, yy);                           // unmodified_vertical (:205-209)
+        if (SC) {
+          const float qo = qold[i][j];
+          if (p.variant == V_SCMS1) {                          // :261-267
+            const bool keep = (qo == 0.0f) || ((qo > 0.0f) == (q > 0.0f) && (qo < 0.0f) == (q < 0.0f));
+            q = keep ? q : 0.0f;
+          } else {                                             // SCMS2 :275-281
+            q = (__fmul_rn(q, qo) > 0.0f) ? q : __fmul_rn(0.5f, __fadd_rn(q, qo));
           }
-          const float a = fabsf(q);
-          m2 = fminf(m2, fmaxf(m1, a));
-          m1 = fminf(m1, a);
-          par ^= __float_as_uint(q);
+          qold[i][j] = q;
+        } else {
+          r[i][j] = q;  // r_j is dead once q_j exists; reuse its register
         }
+        const float a = fabsf(q);
+        m2 = fminf(m2, fmaxf(m1, a));
+        m1 = fminf(m1, a);
+        par ^= __float_as_uint(q);
       }
       m1v[i] = m1;
       f1s[i] = xor_sign(cn_magnitude(p, m1), par);  // fold the row's sign parity in once
@@ -272,16 +279,13 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
       for (int j = W - 1; j >= 0; --j) {
 #pragma unroll
         for (int i = 0; i < RPL; ++i) {
-          int c = row[i] + p.tap[j];
+          int off = T::get(j);
           bool wrapped = false;
-          if (WRAP && c >= n) {
-            c -= n;
+          if (WRAP && row[i] + off >= N) {
+            off -= N;
             wrapped = true;
           }
-          if (rvalid[i] && wrapped == (pass == 1)) {
-            c += colbase;
-            sbuf[c] = __fadd_rn(sbuf[c], r[i][j]);
-          }
+          if (rvalid[i] && wrapped == (pass == 1)) yrow[i][SOFF + off] = __fadd_rn(yrow[i][SOFF + off], r[i][j]);
         }
         __syncwarp();
       }
@@ -310,7 +314,7 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
     const unsigned badm = __ballot_sync(kFull, bad);
     const bool stop = (badm & gmask) == 0u;
     const bool last = it + 1 >= p.max_iter;
-    const bool fin = active && !need_init && (stop || last);
+    const bool fin = active && (stop || last);
     const unsigned finm = __ballot_sync(kFull, fin);
     if (finm) {
       // ---- decided word / totals of the finishing groups
@@ -319,11 +323,12 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
         for (int ps = 0; ps < NP; ++ps) {
           const long long fr = __shfl_sync(kFull, my_frame, cgrp_lead[ps]);
           if (cvalid[ps] && ((finm >> cgrp_lead[ps]) & 1u)) {
-            if (p.bits) p.bits[fr * n + ccol[ps]] = static_cast<uint8_t>((bw[ps] >> lane) & 1u);
-            if (p.L) p.L[fr * n + ccol[ps]] = __fadd_rn(sbuf[lane + 32 * ps], ybuf[lane + 32 * ps]);
+            if (p.bits) p.bits[fr * N + ccol[ps]] = static_cast<uint8_t>((bw[ps] >> lane) & 1u);
+            if (p.L) p.L[fr * N + ccol[ps]] = __fadd_rn(sbuf[lane + 32 * ps], ybuf[lane + 32 * ps]);
           }
         }
       }
+      long long next = 0;
       if (fin) {
         const bool failed = !stop && p.stop_rule != STOP_NONE;
         int nbits = 0;
@@ -338,8 +343,12 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
           cnt_berr += static_cast<unsigned>(nbits);
           cnt_ferr += (failed || nbits != 0) ? 1 : 0;
           cnt_und += (!failed && nbits != 0) ? 1 : 0;
+          next = units + static_cast<long long>(atomicAdd(p.work, 1ull));  // dynamic schedule
         }
-        my_frame += units;
+      }
+      next = __shfl_sync(kFull, next, lead_lane);
+      if (fin) {
+        my_frame = next;
         active = my_frame < static_cast<long long>(p.frames);
         need_init = true;
       }
@@ -359,9 +368,5 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
     }
   }
 }
-
-#define CCGPU_MS_CYCLIC_ENTRY(W, RPL, NP, SC, WRAP)                                                    \
-  { W, RPL, NP, SC, WRAP, reinterpret_cast<ms_kernel_fn>(&ms_cyclic_kernel<W, RPL, NP, (SC) != 0, (WRAP) != 0>), \
-    "ms_cyclic<W=" #W ",RPL=" #RPL ",NP=" #NP ",SC=" #SC ",WRAP=" #WRAP ">" }
 
 }  // namespace ccgpu

@@ -1,7 +1,8 @@
-// ms_cyclic_inst.cu -- compiled once per -DCCGPU_GROUP=g: instantiates the kernels of
-// CCGPU_MS_LIST_g (ms_cyclic_list.h) and exposes them to the registry in ms_registry.cu.
+// ms_cyclic_inst.cu -- compiled once per -DCCGPU_GROUP=g: instantiates ms_cyclic_kernel for the
+// shapes of CCGPU_MS_LIST_g (ms_shapes_generated.h), three vertical-node flavours each, and
+// exposes them to the registry in ms_registry.cu.
 #include "ms_cyclic.cuh"
-#include "ms_cyclic_list.h"
+#include "ms_shapes_generated.h"
 
 #ifndef CCGPU_GROUP
 #error "compile with -DCCGPU_GROUP=<0..CCGPU_MS_GROUPS-1>"
@@ -12,11 +13,28 @@
 #define CCGPU_GROUP_FN CCGPU_CAT(ms_cyclic_group_, CCGPU_GROUP)
 
 namespace ccgpu {
-#define X(W, RPL, NP, WRAP) CCGPU_MS_CYCLIC_ENTRY(W, RPL, NP, 0, WRAP), CCGPU_MS_CYCLIC_ENTRY(W, RPL, NP, 1, WRAP),
+
+template <class S> struct TapTable {
+  int v[S::W];
+  constexpr TapTable() : v{} {
+    for (int j = 0; j < S::W; ++j) v[j] = S::taps::get(j);
+  }
+};
+template <class S> static const TapTable<S> kTapTable{};
+
+template <class S, int VN> MsCyclicEntry make_entry(const char *name) {
+  return MsCyclicEntry{ name, S::N, S::K, S::W, S::RPL, S::FPW, S::NP, S::WRAP ? 1 : 0, VN, kTapTable<S>.v,
+                        reinterpret_cast<ms_kernel_fn>(&ms_cyclic_kernel<S, VN>) };
+}
+
+#define X(NAME) make_entry<shapes::NAME, VN_PLAIN>(#NAME), make_entry<shapes::NAME, VN_SC>(#NAME), \
+                make_entry<shapes::NAME, VN_2D>(#NAME),
 static const MsCyclicEntry kEntries[] = { CCGPU_LIST(X) };
 #undef X
+
 const MsCyclicEntry *CCGPU_GROUP_FN(int *count) {
   *count = static_cast<int>(sizeof(kEntries) / sizeof(kEntries[0]));
   return kEntries;
 }
+
 }  // namespace ccgpu

@@ -12,12 +12,10 @@ enum : int { V_MS = 0, V_NMS = 1, V_OMS = 2, V_SCMS1 = 3, V_SCMS2 = 4, V_NMS2D =
 enum : int { STOP_REF = 0, STOP_GF2 = 1, STOP_NONE = 2 };
 enum : int { SRC_HBM = 0, SRC_PHILOX = 1, SRC_BITFLIP = 2 };
 
-// One launch of a min-sum kernel.  Passed as a __grid_constant__ kernel parameter, so the tap
-// offsets below live in the constant bank and fold into instruction operands after unrolling.
+// One launch of a min-sum kernel (passed as a __grid_constant__ kernel parameter).
 struct MsParams {
-  // ---- parity-check structure: row r has ones at (r + tap[j]) (mod n if wrap), j < w
-  int32_t n, k, w, fpw;  // columns, rows, row weight, frames per warp
-  int16_t tap[kMaxTaps];
+  // ---- parity-check matrix: n columns, k rows (the cyclic kernels know the tap offsets at compile time)
+  int32_t n, k;
   // ---- decoder
   int32_t variant, stop_rule, max_iter, src;
   float alpha_f, beta_f;  // alpha / beta converted double -> float exactly where the reference does
@@ -36,6 +34,7 @@ struct MsParams {
   uint8_t *iter;       // frames
   uint8_t *failed;     // frames
   unsigned long long *counters;  // kCounterSlots, accumulated with atomics
+  unsigned long long *work;      // dynamic frame queue head, zeroed by the host before the launch
 };
 
 // counter slots (ccgpu_counters layout)
@@ -43,14 +42,17 @@ enum : int { C_FRAMES = 0, C_FRAME_ERR = 1, C_BIT_ERR = 2, C_ITER = 3, C_FAIL = 
 
 using ms_kernel_fn = void (*)(MsParams);
 
+// vertical-node flavour a kernel is compiled for
+enum : int { VN_PLAIN = 0 /* MS NMS OMS */, VN_SC = 1 /* SCMS1 SCMS2 */, VN_2D = 2 /* 2DNMS */ };
+
 struct MsCyclicEntry {
-  int w, rpl, np, sc, wrap;
-  ms_kernel_fn fn;
   const char *name;
+  int n, k /* 0: rows at run time */, w, rpl, fpw, np, wrap, vn;
+  const int *taps;
+  ms_kernel_fn fn;
 };
 
-// registry filled by the instantiation units (ms_cyclic_inst_*.cu)
-const MsCyclicEntry *ms_cyclic_find(int w, int rpl, int np, int sc, int wrap);
+// registry filled by the instantiation units (ms_cyclic_inst.cu x CCGPU_GROUP)
 int ms_cyclic_count();
 const MsCyclicEntry *ms_cyclic_at(int i);
 

@@ -1,6 +1,6 @@
 // ms_registry.cu -- lookup over the kernel instantiation groups (ms_cyclic_inst.cu x CCGPU_GROUP).
-#include "ms_cyclic_list.h"
 #include "ms_params.h"
+#include "ms_shapes_generated.h"
 
 namespace ccgpu {
 
@@ -32,17 +32,6 @@ const MsCyclicEntry *ms_cyclic_at(int i) {
     i -= c;
   }
   return nullptr;
-}
-
-// smallest registered shape that can run (w, rpl) with at least np passes
-const MsCyclicEntry *ms_cyclic_find(int w, int rpl, int np, int sc, int wrap) {
-  const MsCyclicEntry *best = nullptr;
-  for (int i = 0, m = ms_cyclic_count(); i < m; ++i) {
-    const MsCyclicEntry *e = ms_cyclic_at(i);
-    if (e->w != w || e->rpl != rpl || e->sc != sc || e->wrap != wrap || e->np < np) continue;
-    if (!best || e->np < best->np) best = e;
-  }
-  return best;
 }
 
 }  // namespace ccgpu
