@@ -31,8 +31,16 @@ struct ccgpu_ctx {
   void *d_stage = nullptr;
   size_t d_stage_bytes = 0;
   unsigned long long *d_counters = nullptr;
-  unsigned long long *d_work = nullptr;  // queue head of the dynamically scheduled kernels
+  unsigned long long *d_work = nullptr;  // queue heads of the dynamically scheduled kernels: [0] main, [1..2] slots
   ccgpu_counters *h_counters = nullptr;  // pinned
+  // host-buffer calls are cut into chunks that alternate between two slots (stream + staging
+  // buffer each), so the H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the decode
+  // of chunk i
+  cudaStream_t slot_stream[2] = { nullptr, nullptr };
+  cudaEvent_t slot_done[2] = { nullptr, nullptr };
+  cudaEvent_t main_ready = nullptr;
+  void *slot_buf[2] = { nullptr, nullptr };
+  size_t slot_bytes = 0;
 };
 
 struct ccgpu_code {
@@ -70,6 +78,23 @@ bool is_device_ptr(const void *p) {
     return false;
   }
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure_slots(ccgpu_ctx *ctx, size_t bytes) {
+  for (int s = 0; s < 2; ++s) {
+    if (!ctx->slot_stream[s]) CU(cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking));
+    if (!ctx->slot_done[s]) CU(cudaEventCreateWithFlags(&ctx->slot_done[s], cudaEventDisableTiming));
+  }
+  if (!ctx->main_ready) CU(cudaEventCreateWithFlags(&ctx->main_ready, cudaEventDisableTiming));
+  if (bytes <= ctx->slot_bytes) return CCGPU_OK;
+  for (int s = 0; s < 2; ++s) {
+    if (ctx->slot_buf[s]) cudaFree(ctx->slot_buf[s]);
+    ctx->slot_buf[s] = nullptr;
+  }
+  ctx->slot_bytes = 0;
+  for (int s = 0; s < 2; ++s) CU(cudaMalloc(&ctx->slot_buf[s], bytes));
+  ctx->slot_bytes = bytes;
+  return CCGPU_OK;
 }
 
 int ensure_stage(ccgpu_ctx *ctx, size_t bytes) {
@@ -178,23 +203,24 @@ void fill_decoder(MsParams &mp, const ccgpu_code *c, const ccgpu_ms_params *p) {
 }
 
 // launch the min-sum decoder for one batch described by mp (source/outputs already filled)
-int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsParams mp) {
+int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsParams mp, int slot = -1) {
   if (mp.frames == 0) return CCGPU_OK;
+  cudaStream_t stream = slot < 0 ? ctx->stream : ctx->slot_stream[slot];
+  unsigned long long *work = ctx->d_work + (slot + 1);
   const int vn = (p->variant == CCGPU_SCMS1 || p->variant == CCGPU_SCMS2) ? VN_SC : (p->variant == CCGPU_NMS2D ? VN_2D : VN_PLAIN);
   if (p->variant != CCGPU_SPA && c->cyc[vn]) {
     const MsCyclicEntry *e = c->cyc[vn];
     const uint64_t per_cta = uint64_t(kMsThreads / 32) * e->fpw;
     const uint64_t want = (mp.frames + per_cta - 1) / per_cta;
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(want, c->grid_max[vn]));
-    CU(cudaMemsetAsync(ctx->d_work, 0, sizeof(unsigned long long), ctx->stream));
-    mp.work = ctx->d_work;
+    CU(cudaMemsetAsync(work, 0, sizeof(unsigned long long), stream));
+    mp.work = work;
     void *args[] = { &mp };
-    CU(cudaLaunchKernel(reinterpret_cast<const void *>(e->fn), dim3(grid), dim3(kMsThreads), args, c->smem[vn],
-                        ctx->stream));
+    CU(cudaLaunchKernel(reinterpret_cast<const void *>(e->fn), dim3(grid), dim3(kMsThreads), args, c->smem[vn], stream));
     ctx->launches++;
     return CCGPU_OK;
   }
-  int rc = ms_csr_launch(c->csr, mp, ctx->sm_count, ctx->stream);
+  int rc = ms_csr_launch(c->csr, mp, ctx->sm_count, stream);
   if (rc == -3) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "parity-check matrix too large for the CSR kernel");
   if (rc != 0) return cuda_fail(ctx, cudaGetLastError(), "ms_csr_launch");
   ctx->launches++;
@@ -221,7 +247,7 @@ int ccgpu_create(int device, ccgpu_ctx **out) {
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
       cudaMalloc(&ctx->d_counters, sizeof(ccgpu_counters)) != cudaSuccess ||
-      cudaMalloc(&ctx->d_work, sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_work, 3 * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMallocHost(&ctx->h_counters, sizeof(ccgpu_counters)) != cudaSuccess) {
     cudaGetLastError();
     delete ctx;
@@ -238,6 +264,15 @@ void ccgpu_destroy(ccgpu_ctx *ctx) {
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->d_work) cudaFree(ctx->d_work);
+  for (int s = 0; s < 2; ++s) {
+    if (ctx->slot_stream[s]) {
+      cudaStreamSynchronize(ctx->slot_stream[s]);
+      cudaStreamDestroy(ctx->slot_stream[s]);
+    }
+    if (ctx->slot_done[s]) cudaEventDestroy(ctx->slot_done[s]);
+    if (ctx->slot_buf[s]) cudaFree(ctx->slot_buf[s]);
+  }
+  if (ctx->main_ready) cudaEventDestroy(ctx->main_ready);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -444,34 +479,38 @@ int ccgpu_decode_llr(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_para
     mp.failed = failed;
     return launch_ms(ctx, code, params, mp);
   }
-  // host buffers: stage in chunks so H2D of chunk i+1 can overlap the decode of chunk i
+  // host buffers: chunks alternate between two slots so that copies and decoding overlap
   const size_t per_frame = n * sizeof(float) + n + (L ? n * sizeof(float) : 0) + 2;
-  const uint64_t chunk = std::min<uint64_t>(frames, std::max<uint64_t>(1, (size_t(256) << 20) / per_frame));
-  rc = ensure_stage(ctx, chunk * per_frame + 64);
+  const uint64_t chunk = std::max<uint64_t>(1024, std::min<uint64_t>((frames + 7) / 8, (size_t(64) << 20) / per_frame));
+  rc = ensure_slots(ctx, chunk * per_frame + 256);
   if (rc) return rc;
-  char *base = static_cast<char *>(ctx->d_stage);
-  float *d_y = reinterpret_cast<float *>(base);
-  float *d_L = L ? reinterpret_cast<float *>(base + chunk * n * sizeof(float)) : nullptr;
-  uint8_t *d_bits = reinterpret_cast<uint8_t *>(base + chunk * n * sizeof(float) * (L ? 2 : 1));
-  uint8_t *d_iter = d_bits + chunk * n;
-  uint8_t *d_failed = d_iter + chunk;
-  for (uint64_t f0 = 0; f0 < frames; f0 += chunk) {
+  CU(cudaEventRecord(ctx->main_ready, ctx->stream));
+  for (int s = 0; s < 2; ++s) CU(cudaStreamWaitEvent(ctx->slot_stream[s], ctx->main_ready, 0));
+  int slot = 0;
+  for (uint64_t f0 = 0; f0 < frames; f0 += chunk, slot ^= 1) {
     const uint64_t nf = std::min(chunk, frames - f0);
-    CU(cudaMemcpyAsync(d_y, y + f0 * n, nf * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    cudaStream_t st = ctx->slot_stream[slot];
+    char *base = static_cast<char *>(ctx->slot_buf[slot]);
+    float *d_y = reinterpret_cast<float *>(base);
+    float *d_L = L ? reinterpret_cast<float *>(base + chunk * n * sizeof(float)) : nullptr;
+    uint8_t *d_bits = reinterpret_cast<uint8_t *>(base + chunk * n * sizeof(float) * (L ? 2 : 1));
+    uint8_t *d_iter = d_bits + chunk * n;
+    uint8_t *d_failed = d_iter + chunk;
+    CU(cudaMemcpyAsync(d_y, y + f0 * n, nf * n * sizeof(float), cudaMemcpyHostToDevice, st));
     mp.y = d_y;
     mp.bits = d_bits;
     mp.L = d_L;
     mp.iter = d_iter;
     mp.failed = d_failed;
     mp.frames = nf;
-    rc = launch_ms(ctx, code, params, mp);
+    rc = launch_ms(ctx, code, params, mp, slot);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(bits + f0 * n, d_bits, nf * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (L) CU(cudaMemcpyAsync(L + f0 * n, d_L, nf * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    if (iter) CU(cudaMemcpyAsync(iter + f0, d_iter, nf, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(failed + f0, d_failed, nf, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(bits + f0 * n, d_bits, nf * n, cudaMemcpyDeviceToHost, st));
+    if (L) CU(cudaMemcpyAsync(L + f0 * n, d_L, nf * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (iter) CU(cudaMemcpyAsync(iter + f0, d_iter, nf, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(failed + f0, d_failed, nf, cudaMemcpyDeviceToHost, st));
   }
-  CU(cudaStreamSynchronize(ctx->stream));
+  for (int s = 0; s < 2; ++s) CU(cudaStreamSynchronize(ctx->slot_stream[s]));
   return CCGPU_OK;
 }
 
