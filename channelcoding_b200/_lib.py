@@ -75,6 +75,12 @@ def lib():
     L.ccgpu_decode_llr.argtypes = [vp, vp, C.POINTER(MsParams), vp, u64, vp, vp, vp, vp]
     L.ccgpu_sigma.argtypes = [dbl, dbl]
     L.ccgpu_sigma.restype = dbl
+    L.ccgpu_shannon_limit_db.argtypes = [dbl]
+    L.ccgpu_shannon_limit_db.restype = dbl
+    L.ccgpu_sweep_start_ebno.argtypes = [dbl, dbl]
+    L.ccgpu_sweep_start_ebno.restype = dbl
+    L.ccgpu_sweep_samples.argtypes = [dbl, u64]
+    L.ccgpu_sweep_samples.restype = u64
     L.ccgpu_awgn_llr.argtypes = [vp, u32, dbl, u64, u32, u64, u64, vp]
     L.ccgpu_awgn_point.argtypes = [vp, vp, C.POINTER(MsParams), dbl, u64, u32, u64, u64, vp]
     L.ccgpu_bitflip_point.argtypes = [vp, vp, C.POINTER(MsParams), u32, u64, u64, vp]
@@ -90,5 +96,5 @@ EXPORTS = ["ccgpu_abi_version", "ccgpu_create", "ccgpu_destroy", "ccgpu_last_err
            "ccgpu_get_stream", "ccgpu_sync", "ccgpu_kernel_launches", "ccgpu_bch_create", "ccgpu_rs_create",
            "ccgpu_code_from_dense", "ccgpu_code_set_rows", "ccgpu_code_destroy", "ccgpu_code_get_info",
            "ccgpu_code_to_string", "ccgpu_code_H", "ccgpu_code_poly", "ccgpu_gf_tables", "ccgpu_encode",
-           "ccgpu_decode_llr", "ccgpu_sigma", "ccgpu_awgn_llr", "ccgpu_awgn_point", "ccgpu_bitflip_point",
+           "ccgpu_decode_llr", "ccgpu_sigma", "ccgpu_shannon_limit_db", "ccgpu_sweep_start_ebno", "ccgpu_sweep_samples", "ccgpu_awgn_llr", "ccgpu_awgn_point", "ccgpu_bitflip_point",
            "ccgpu_gf_decode"]

@@ -72,6 +72,36 @@ def build(force=False, verbose=False):
     return LIB
 
 
+TOOLS_BIN = os.path.join(os.path.dirname(HERE), "tools", "_bin")
+
+
+def build_tools(force=False):
+    """the C++ host layer (include/cc/*.h) in use: the reference-style `benchmark` CLI and the C++
+    test program, linked against libccgpu.so (g++; no CUDA code in these)."""
+    root = os.path.dirname(HERE)
+    os.makedirs(TOOLS_BIN, exist_ok=True)
+    hdrs = [os.path.join(root, "include", "ccgpu.h"), os.path.join(root, "include", "cc", "codes.h"),
+            os.path.join(root, "include", "cc", "simulation.h")]
+    jobs = [(os.path.join(TOOLS_BIN, "benchmark"), os.path.join(root, "tools", "benchmark.cc")),
+            (os.path.join(TOOLS_BIN, "host_layer_test"), os.path.join(root, "tests", "cpp", "host_layer_test.cc"))]
+
+    def one(job):
+        out, src = job
+        newest = max(os.path.getmtime(p) for p in hdrs + [src, LIB])
+        if not force and os.path.exists(out) and os.path.getmtime(out) >= newest:
+            return out
+        cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I" + os.path.join(root, "include"), src, "-L" + HERE, "-lccgpu",
+               "-Wl,-rpath,$ORIGIN/../../channelcoding_b200", "-pthread", "-o", out]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed for %s:\n%s" % (src, r.stdout + r.stderr))
+        return out
+    with concurrent.futures.ThreadPoolExecutor(max_workers=2) as ex:
+        return list(ex.map(one, jobs))
+
+
 if __name__ == "__main__":
     path = build(force="--force" in sys.argv, verbose="-v" in sys.argv)
     print(path)
+    if "--tools" in sys.argv:
+        print(build_tools(force="--force" in sys.argv))

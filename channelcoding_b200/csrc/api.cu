@@ -453,6 +453,43 @@ double ccgpu_sigma(double rate, double ebno_db) {
   return 1.0f / std::sqrt(2 * rate * std::pow(10, ebno_db / 10.0));
 }
 
+static double biawgn_capacity(double snr) {  // bit/use at Es/N0 = snr (linear); LLR ~ N(4 snr, 8 snr)
+  const double mean = 4.0 * snr, sd = std::sqrt(8.0 * snr);
+  const int steps = 4000;
+  const double lo = mean - 10 * sd, hi = mean + 10 * sd, dx = (hi - lo) / steps;
+  double acc = 0;
+  for (int i = 0; i <= steps; ++i) {
+    const double x = lo + i * dx;
+    const double pdf = std::exp(-0.5 * (x - mean) * (x - mean) / (sd * sd)) / (sd * std::sqrt(2 * M_PI));
+    const double f = (x > 30 ? std::exp(-x) : std::log1p(std::exp(-x))) / std::log(2.0);
+    acc += (i == 0 || i == steps ? 0.5 : 1.0) * pdf * f * dx;
+  }
+  return 1.0 - acc;
+}
+
+double ccgpu_shannon_limit_db(double rate) {
+  if (!(rate > 0.0)) return -1.59;
+  const double r = rate <= 0.8 ? (std::floor(rate * 100) + 1) / 100.0 : std::min(rate, 0.999);
+  double lo = -3.0, hi = 12.0;
+  for (int i = 0; i < 60; ++i) {
+    const double mid = 0.5 * (lo + hi);
+    if (biawgn_capacity(r * std::pow(10.0, mid / 10.0)) < r) lo = mid;
+    else hi = mid;
+  }
+  return 0.5 * (lo + hi);
+}
+
+double ccgpu_sweep_start_ebno(double rate, double step) {
+  const double lim = std::max(0.0, ccgpu_shannon_limit_db(rate));
+  const size_t tmp = static_cast<size_t>(lim / step);
+  return (tmp + (1.0 / step)) * step;
+}
+
+uint64_t ccgpu_sweep_samples(double previous_wer, uint64_t cap) {
+  if (!(previous_wer > 0.0)) return cap;
+  return static_cast<uint64_t>(std::min(static_cast<double>(cap), 5e3 / previous_wer));
+}
+
 // ---- decoding ----------------------------------------------------------------------------------
 int ccgpu_decode_llr(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, const float *y,
                      uint64_t frames, uint8_t *bits, float *L, uint8_t *iter, uint8_t *failed) {

@@ -159,6 +159,16 @@ int ccgpu_decode_llr(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_para
 
 /* sigma of simulation.c++:83-85: 1 / sqrt(2 * rate * 10^(ebno_db/10)) */
 double ccgpu_sigma(double rate, double ebno_db);
+/* Shannon limit Eb/N0 [dB] of the binary-input AWGN channel at `rate`: replaces the lookup ebno(rate)
+ * of simulation.c++:56-70 in the tables :21-52.  Like that lookup, rates <= 0.8 are first rounded up
+ * to the next multiple of 0.01.  Computed (numerical capacity integral + bisection), not tabulated. */
+double ccgpu_shannon_limit_db(double rate);
+/* first Eb/N0 point of a sweep, simulation.c++:105-107: (size_t(limit / step) + 1 / step) * step,
+ * a negative limit counting as 0 */
+double ccgpu_sweep_start_ebno(double rate, double step);
+/* frames to simulate at a point given the previous point's word error rate, simulation.c++:91-93:
+ * min(cap, 5e3 / wer); cap is 1e6 in the reference */
+uint64_t ccgpu_sweep_samples(double previous_wer, uint64_t cap);
 
 /* channel only: y[f][c] = 1 + sigma * z, z ~ N(0,1) from Philox4x32-10 keyed (seed, point),
  * counter (frame0 + f, c / 4)  -- replaces std::generate(b, noise) of simulation.c++:113-115, :125 */

@@ -1,0 +1,174 @@
+// tests/cpp/host_layer_test.cc -- exercises the C++ drop-in layer (include/cc/*.h) the way the
+// reference's own programs use their classes (exercises.c++, bitflips.c++, benchmark.c++).
+//   host_layer_test --host        no GPU needed: tags, capabilities, sweep start rule
+//   host_layer_test --gpu <dir>   needs a B200: correct(), decoding_failure, to_string, bit-flip KAT,
+//                                 awgn sweep log format
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "cc/simulation.h"
+
+using namespace cc;
+
+#define CHECK(cond)                                                                  \
+  do {                                                                               \
+    if (!(cond)) {                                                                   \
+      std::cerr << "CHECK failed: " #cond " at line " << __LINE__ << std::endl;      \
+      return 1;                                                                      \
+    }                                                                                \
+  } while (0)
+
+static int host_tests() {
+  // codes/codes.h:15-26
+  static_assert(correction_capability<dmin<7> >::value == 3, "");
+  static_assert(correction_capability<dmin<6> >::value == 2, "");
+  static_assert(correction_capability<errors<5> >::value == 5, "");
+  // tag names (soft_decision.h:20-73, hard_decision.h:15-24)
+  CHECK(min_sum_tag<50>::to_string() == "MS");
+  CHECK((normalized_min_sum_tag<50, std::ratio<8, 10> >::to_string() == "NMS"));
+  CHECK((offset_min_sum_tag<50, std::ratio<1, 100> >::to_string() == "OMS"));
+  CHECK(self_correcting_1_min_sum_tag<50>::to_string() == "SCMS1");
+  CHECK(self_correcting_2_min_sum_tag<50>::to_string() == "SCMS2");
+  CHECK(normalized_2d_min_sum_tag<50>::to_string() == "2DNMS");
+  CHECK(berlekamp_massey_tag::to_string() == "BM" && euklid_tag::to_string() == "EUKLID" &&
+        peterson_gorenstein_zierler_tag::to_string() == "PGZ");
+  CHECK((normalized_min_sum_tag<50, std::ratio<8, 10> >::alpha == 0.8));
+  CHECK((offset_min_sum_tag<50, std::ratio<1, 100> >::beta == 0.01));
+  // the reference's 2DNMS default is alpha = beta = 1 (soft_decision.h:71)
+  CHECK(normalized_2d_min_sum_tag<50>::alpha == 1.0 && normalized_2d_min_sum_tag<50>::beta == 1.0);
+  CHECK((normalized_2d_min_sum_tag<50, std::ratio<968, 1000>, std::ratio<907, 1000> >::beta == 907.0 / 125.0));
+  // sweep start, simulation.c++:105-107 with the Shannon-limit table :21-52 (values from SURVEY 8d)
+  CHECK(awgn_simulation::start_ebno(36.0 / 63, 0.5) == 1.5);
+  CHECK(awgn_simulation::start_ebno(7.0 / 15, 0.5) == 1.0);
+  CHECK(awgn_simulation::start_ebno(64.0 / 127, 0.5) == 1.0);
+  CHECK(awgn_simulation::start_ebno(131.0 / 255, 0.5) == 1.0);
+  CHECK(std::fabs(ccgpu_shannon_limit_db(0.495) - 0.188) < 0.003);  // table: rate 0.50 -> 0.188 dB
+  CHECK(std::fabs(ccgpu_shannon_limit_db(0.795) - 2.045) < 0.01);   // table: rate 0.80 -> 2.045 dB
+  CHECK(std::fabs(ccgpu_shannon_limit_db(0.005) - (-1.548)) < 0.02); // table: rate 0.01 -> -1.548 dB
+  std::cout << "host tests ok" << std::endl;
+  return 0;
+}
+
+static int gpu_tests(const std::string &dir) {
+  // exercises.c++ task 6.1: primitive_bch<4, dmin<7>> corrects b1 and b2 to a
+  {
+    primitive_bch<4, dmin<7> > code;
+    const std::vector<unsigned char> a({ 1, 1, 1, 0, 0, 0, 1, 0, 0, 1, 1, 0, 1, 0, 1 });
+    std::vector<unsigned> b1({ 1, 1, 1, 1, 0, 0, 1, 0, 0, 1, 0, 0, 1, 1, 1 });
+    std::vector<unsigned> b2({ 1, 1, 1, 1, 0, 0, 1, 0, 0, 1, 0, 0, 1, 0, 1 });
+    CHECK(code.correct(b1) == a);
+    CHECK(code.correct(b2) == a);
+    CHECK(code.to_string() == "(15, 5, 7)-PGZ");
+    CHECK(decltype(code)::n == 15 && decltype(code)::t == 3);
+  }
+  // task 6.2: decoding failure is an exception of type decoding_failure
+  {
+    primitive_bch<4, dmin<5> > code;
+    const std::vector<unsigned> b({ 1, 0, 0, 1, 0, 1, 1, 1, 1, 0, 1, 1, 0, 0, 0 });
+    bool threw = false;
+    try {
+      code.correct(b);
+    } catch (const decoding_failure &) {
+      threw = true;
+    }
+    CHECK(threw);
+  }
+  // task 6.10: three algorithm tags, one answer
+  {
+    const std::vector<uint8_t> a({ 1, 0, 1, 0, 0, 1, 1, 1, 1, 0, 1, 1, 1, 1, 1 });
+    const std::vector<uint8_t> want({ 1, 0, 1, 0, 0, 1, 1, 1, 1, 0, 1, 0, 1, 0, 1 });
+    CHECK((primitive_bch<4, errors<2>, peterson_gorenstein_zierler_tag>().correct(a) == want));
+    CHECK((primitive_bch<4, errors<2>, berlekamp_massey_tag>().correct(a) == want));
+    CHECK((primitive_bch<4, errors<2>, euklid_tag>().correct(a) == want));
+  }
+  // RS(255,223) through the same interface
+  {
+    rs<8, errors<16>, euklid_tag> code;
+    CHECK(code.to_string() == "(255, 223, 34)-EUKLID");  // sic: dmin as the reference computes it
+    std::vector<uint8_t> w(255, 0);
+    w[3] = 7; w[100] = 200; w[254] = 1;
+    CHECK(code.correct(w) == std::vector<uint8_t>(255, 0));
+  }
+  // soft decoders through the type-erased decoder, like simulation.c++:124-136
+  {
+    decoder d = primitive_bch<6, errors<5>, normalized_min_sum_tag<50, std::ratio<8, 10> > >();
+    CHECK(d.to_string() == "(63, 36, 11)-NMS" && d.n() == 63 && std::fabs(d.rate() - 36.0 / 63) < 1e-15);
+    std::vector<float> y(63, 1.0f);
+    y[5] = -0.4f;
+    const auto r = d.correct(y);
+    CHECK(r == std::vector<uint8_t>(63, 0));
+    std::vector<float> bad(63, -1.0f);  // the all-one word never satisfies the reference's stop rule
+    bool threw = false;
+    try {
+      d.correct(bad);
+    } catch (const decoding_failure &) {
+      threw = true;
+    }
+    CHECK(threw);
+    bool size_error = false;
+    try {
+      d.correct(std::vector<float>(10, 1.0f));
+    } catch (const std::runtime_error &) {
+      size_error = true;
+    }
+    CHECK(size_error);
+  }
+  // bitflips.c++ on (31,16,7): failures per weight and the log format
+  {
+    decoder ms = primitive_bch<5, dmin<7>, min_sum_tag<50> >();
+    decoder bm = primitive_bch<5, dmin<7>, berlekamp_massey_tag>();
+    CHECK(ms.bitflip_point(2).frame_errors == 138 && ms.bitflip_point(3).frame_errors == 3557);
+    CHECK(bm.bitflip_point(3).frame_errors == 0 && bm.bitflip_point(4).frame_errors == 31465);
+    bitflip_simulation(ms, 3).output_dir(dir)();
+    std::ifstream f(dir + "/(31, 16, 7)-MS.log");
+    std::stringstream ss;
+    ss << f.rdbuf();
+    const std::string expect = " errors                   wer\n"
+                               "      0 0.000000000000000e+00\n"
+                               "      1 0.000000000000000e+00\n"
+                               "      2 2.967741935483871e-01\n"
+                               "      3 7.913236929922135e-01\n";
+    if (ss.str() != expect) std::cerr << "got:\n" << ss.str() << "want:\n" << expect;
+    CHECK(ss.str() == expect);
+    bool refused = false;  // simulation.c++:72-81: an existing log is never overwritten
+    try {
+      bitflip_simulation(ms, 1).output_dir(dir)();
+    } catch (const std::runtime_error &) {
+      refused = true;
+    }
+    CHECK(refused);
+  }
+  // awgn sweep: schedule and log format (simulation.c++:95-150)
+  {
+    decoder d = primitive_bch<4, errors<2>, min_sum_tag<50> >();
+    awgn_simulation(d, 0.5, 0).samples_cap(200000).output_dir(dir)();
+    std::ifstream f(dir + "/(15, 7, 5)-MS.log");
+    std::string line;
+    std::getline(f, line);
+    CHECK(line == "   ebno                   wer");
+    int points = 0;
+    double first = -1, last_wer = 1.0;
+    while (std::getline(f, line)) {
+      double eb, wer;
+      std::istringstream(line) >> eb >> wer;
+      if (points == 0) first = eb;
+      CHECK(wer <= last_wer * 1.5 + 1e-3);  // a waterfall
+      last_wer = wer;
+      ++points;
+    }
+    CHECK(first == 1.0 && points == 15);  // 1.0, 1.5, .., 8.0
+    CHECK(last_wer < 1e-3);
+  }
+  std::cout << "gpu tests ok" << std::endl;
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  if (argc >= 2 && std::string(argv[1]) == "--host") return host_tests();
+  if (argc >= 3 && std::string(argv[1]) == "--gpu") return gpu_tests(argv[2]);
+  std::cerr << "usage: host_layer_test --host | --gpu <scratch dir>" << std::endl;
+  return 2;
+}

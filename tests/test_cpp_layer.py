@@ -1,0 +1,59 @@
+"""The C++ drop-in layer (include/cc/codes.h, include/cc/simulation.h) and the reference-style CLI
+(tools/benchmark.cc), built by channelcoding_b200.build.build_tools()."""
+import os
+import subprocess
+
+import pytest
+
+from channelcoding_b200 import build as _build
+
+
+@pytest.fixture(scope="module")
+def bins():
+    _build.build()
+    outs = _build.build_tools()
+    return {os.path.basename(p): p for p in outs}
+
+
+def test_host_part(bins):
+    r = subprocess.run([bins["host_layer_test"], "--host"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_cli_usage_without_selection(bins):
+    """an empty selection prints the usage like benchmark.c++:434-437 -- but first the catalogue has to be
+    constructed, which needs the GPU: on a CPU-only box the program must fail loudly, not fall back"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([bins["benchmark"], "--k", "5"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0
+    assert "no usable CUDA device" in (r.stdout + r.stderr)
+
+
+@pytest.mark.gpu
+def test_gpu_part(bins, tmp_path):
+    r = subprocess.run([bins["host_layer_test"], "--gpu", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_bitflip_and_awgn(bins, tmp_path, kat):
+    """benchmark --simulation bitflip reproduces Table 3 counts; --simulation awgn writes the sweep log"""
+    r = subprocess.run([bins["benchmark"], "--simulation", "bitflip", "--k", "5", "--dmin", "7", "--algorithm", "ms",
+                        "--algorithm", "scms2", "--algorithm", "bm", "--errors", "3", "--out", str(tmp_path)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for tag, key in (("MS", "MS"), ("SCMS2", "SCMS2"), ("BM", "BM")):
+        lines = open(tmp_path / ("(31, 16, 7)-%s.log" % tag)).read().splitlines()
+        assert lines[0] == " errors                   wer"
+        for w in range(4):
+            row = kat["bitflip_31_16_7"][str(w)]
+            assert abs(float(lines[1 + w].split()[1]) - row[key] / row["patterns"]) < 1e-12
+    r = subprocess.run([bins["benchmark"], "--k", "6", "--dmin", "7", "--algorithm", "nms", "--max-samples", "100000",
+                        "--seed", "3", "--out", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = open(tmp_path / "(63, 45, 7)-NMS.log").read().splitlines()
+    assert lines[0] == "   ebno                   wer" and len(lines) >= 10
+    wers = [float(x.split()[1]) for x in lines[1:]]
+    assert wers[0] > 0.3 and wers[-1] < 1e-3
