@@ -130,7 +130,7 @@ static int gpu_tests(const std::string &dir) {
                                "      0 0.000000000000000e+00\n"
                                "      1 0.000000000000000e+00\n"
                                "      2 2.967741935483871e-01\n"
-                               "      3 7.913236929922135e-01\n";
+                               "      3 7.913236929922136e-01\n";
     if (ss.str() != expect) std::cerr << "got:\n" << ss.str() << "want:\n" << expect;
     CHECK(ss.str() == expect);
     bool refused = false;  // simulation.c++:72-81: an existing log is never overwritten

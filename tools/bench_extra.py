@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""tools/bench_extra.py -- throughput of the other BASELINE.json configurations (bench.py covers the
+headline one): fused Monte-Carlo points for BCH(15,7) / (63,36) / (127,64) [H() and redundant H] /
+(255,131), and the batched RS(255,223) algebraic decode, each next to the reference's CPU decoder on
+the host cores.  Prints one JSON line per measurement.
+
+    python tools/bench_extra.py [--quick] [--no-cpu]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=4.0)
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    import channelcoding_b200 as cc
+    ctx = cc.Context(0)
+    ctx.use_torch_stream()
+    ref = None
+    if not args.no_cpu:
+        import ccref
+        if ccref.available():
+            ref = ccref.Ref()
+    cores = os.cpu_count()
+
+    def fused(name, code, ebno, frames, variant, alpha=1.0, beta=0.0, stop=0, refkey=None, label=""):
+        out = torch.zeros(8, dtype=torch.int64, device="cuda")
+        code.awgn_point(ebno, min(frames, 100000), variant, alpha, beta, 50, stop, out=out)  # warm-up
+        torch.cuda.synchronize()
+        out.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        code.awgn_point(ebno, frames, variant, alpha, beta, 50, stop, seed=1, point=7, out=out)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        c = out.cpu().numpy()
+        line = {"config": name, "path": "fused awgn_point" + label, "ebno_db": ebno, "variant": variant, "frames": int(c[0]),
+                "frames_per_s": frames / (ms * 1e-3), "info_bits_per_s": frames / (ms * 1e-3) * code.l, "ms": ms,
+                "wer": float(c[1]) / frames, "ber": float(c[2]) / frames / code.n, "avg_iterations": float(c[3]) / frames,
+                "kernel": {1: "ms_cyclic", 2: "ms_csr"}[code.kernel]}
+        if ref is not None and refkey is not None:
+            f, w, el = ref.awgn_baseline(*refkey, ebno, seed=0, seconds=args.cpu_seconds, threads=cores)
+            line["cpu_reference"] = {"frames_per_s": f / el, "cores": cores, "wer": w / f, "frames": f}
+            line["speedup_vs_cpu"] = line["frames_per_s"] / (f / el)
+        print(json.dumps(line), flush=True)
+
+    scale = 0.1 if args.quick else 1.0
+    from ccref import ALG_SOFT0, CAP_ERRORS, FAM_BCH
+    c15 = ctx.bch(4, errors=2)
+    for eb in (1.0, 3.0, 6.0):
+        fused("BCH(15,7) MS", c15, eb, int(2e7 * scale), "MS", refkey=(FAM_BCH, 4, CAP_ERRORS, 2, ALG_SOFT0 + 0))
+    c63 = ctx.bch(6, errors=5)
+    for eb in (2.0, 4.0, 6.0):
+        fused("BCH(63,36) NMS", c63, eb, int(2e7 * scale), "NMS", 0.8, refkey=(FAM_BCH, 6, CAP_ERRORS, 5, ALG_SOFT0 + 1))
+    fused("BCH(63,36) NMS gf2-stop", c63, 4.0, int(2e7 * scale), "NMS", 0.8, stop=1)
+    for v, a, b in (("MS", 1, 0), ("OMS", 1, 0.01), ("SCMS1", 1, 0), ("SCMS2", 1, 0), ("2DNMS", 0.9, 0.9)):
+        fused("BCH(63,36) " + v, c63, 4.0, int(1e7 * scale), v, a, b)
+    c127 = ctx.bch(7, errors=10)
+    for eb in (3.0, 5.0):
+        fused("BCH(127,64) NMS", c127, eb, int(4e6 * scale), "NMS", 0.8, refkey=(FAM_BCH, 7, CAP_ERRORS, 10, ALG_SOFT0 + 1))
+    c127.set_rows(127)
+    fused("BCH(127,64) NMS redundant H (127 rows)", c127, 4.0, int(2e6 * scale), "NMS", 0.8, stop=1, label=", redundant")
+    c127.set_rows(63)
+    fused("BCH(127,64) NMS gf2-stop", c127, 4.0, int(2e6 * scale), "NMS", 0.8, stop=1)
+    c255 = ctx.bch(8, errors=18)
+    for eb in (4.0, 6.0):
+        fused("BCH(255,131) NMS", c255, eb, int(2e5 * scale), "NMS", 0.8, refkey=(FAM_BCH, 8, CAP_ERRORS, 18, ALG_SOFT0 + 1))
+
+    # ---- RS(255,223): 1e7 codewords, error count uniform 0..16 plus a beyond-t slice
+    rs = ctx.rs(8, 16)
+    count = int(1e7 * scale)
+    rng = np.random.default_rng(5)
+    base = 4096
+    msgs = rng.integers(0, 256, size=(base, rs.l)).astype(np.uint8)
+    words = rs.encode(msgs)
+    bad = words.copy()
+    ne = rng.integers(0, 18, size=base)
+    for i in range(base):
+        pos = rng.choice(255, ne[i], replace=False)
+        bad[i, pos] ^= rng.integers(1, 256, size=ne[i]).astype(np.uint8)
+    reps = (count + base - 1) // base
+    d_words = torch.from_numpy(bad).cuda().repeat(reps, 1)[:count].contiguous()
+    out = (torch.empty_like(d_words), torch.empty(count, dtype=torch.uint8, device="cuda"),
+           torch.empty(count, dtype=torch.uint8, device="cuda"))
+    rs.gf_decode(d_words[:100000], out=(out[0][:100000], out[1][:100000], out[2][:100000]))
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rs.gf_decode(d_words, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    ok = out[2][:base].cpu().numpy() == 0
+    assert np.array_equal(out[0][:base].cpu().numpy()[ok], words[ok]) and ok[ne <= 16].all() and not ok[ne > 16].any()
+    line = {"config": "RS(255,223) hard decode", "path": "gf_decode resident", "codewords": count,
+            "codewords_per_s": count / (ms * 1e-3), "ms": ms, "bytes_per_codeword": 511,
+            "hbm_GBps": count * 511 / (ms * 1e-3) / 1e9}
+    h_words = d_words[: count // 4].cpu().pin_memory().numpy()
+    h_out = (np.empty_like(h_words), np.empty(len(h_words), np.uint8), np.empty(len(h_words), np.uint8))
+    t0 = time.perf_counter()
+    rs.gf_decode(h_words, out=h_out)
+    line["e2e_codewords_per_s"] = len(h_words) / (time.perf_counter() - t0)
+    if ref is not None:
+        from ccref import ALG_EUKLID, FAM_RS
+        t0 = time.perf_counter()
+        ref.hard_correct(FAM_RS, 8, CAP_ERRORS, 16, ALG_EUKLID, bad[:2048])
+        el = time.perf_counter() - t0
+        line["cpu_reference"] = {"codewords_per_s_one_core": 2048 / el, "cores_used": 1,
+                                 "note": "euklid_tag, stdout of rs.h:53-75 silenced"}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
