@@ -24,6 +24,8 @@ mkdir -p "$OUT"
 # up to date?
 if [ -f "$OUT/libccref.so" ] && [ -f "$OUT/libccref_head.so" ] \
    && [ "$OUT/libccref.so" -nt "$HERE/ref_shim.cc" ] && [ "$OUT/libccref.so" -nt "$HERE/build_ref.sh" ] \
+   && [ -f "$OUT/integration_test" ] && [ "$OUT/integration_test" -nt "$HERE/integration_test.cc" ] \
+   && [ "$OUT/integration_test" -nt "$HERE/gpu_decoder.h" ] \
    && [ "${1:-}" != "--force" ]; then
   echo "build_ref: up to date"; exit 0
 fi
@@ -73,5 +75,12 @@ EOF
 SRCS_FIXED="$HERE/ref_shim.cc $SCRATCH/src_fixed/codes/codes.c++ $SCRATCH/src_fixed/simulation/simulation.c++"
 g++ $CXXFLAGS -I"$SCRATCH/src_fixed" -shared -o "$OUT/libccref.so" -x c++ $SRCS_FIXED
 wait $HEAD_PID
+# the INTEGRATION.md adapter compiled against the real reference headers (needs libccgpu.so to link)
+LIBDIR="$HERE/../channelcoding_b200"
+if [ -f "$LIBDIR/libccgpu.so" ]; then
+  g++ $CXXFLAGS -I"$SCRATCH/src_fixed" -I"$HERE" -I"$HERE/../include" "$HERE/integration_test.cc" \
+      "$SCRATCH/src_fixed/codes/codes.c++" "$SCRATCH/src_fixed/simulation/simulation.c++" \
+      -L"$LIBDIR" -lccgpu -Wl,-rpath,'$ORIGIN/../../channelcoding_b200' -o "$OUT/integration_test"
+fi
 ls -la "$OUT"
 echo "build_ref: done"
