@@ -152,17 +152,17 @@ void select_cyclic(ccgpu_code *c) {
     const MsCyclicEntry *e = ms_cyclic_at(i);
     if (e->n != n || e->w != w || !std::equal(c->shape.taps.begin(), c->shape.taps.end(), e->taps)) continue;
     const bool exact = e->k == k && !e->wrap && c->shape.kind == 0;
-    const bool redundant = e->k == 0 && e->wrap && k <= 32 * e->rpl;
+    const bool redundant = e->k == 0 && e->wrap && k <= (e->cta ? e->threads : 32) * e->rpl;
     if (!exact && !redundant) continue;
     if (c->cyc[e->vn] && !exact) continue;  // an exact shape wins over the redundant one
     c->cyc[e->vn] = e;
   }
   for (int vn = 0; vn < 3; ++vn) {
     if (!c->cyc[vn]) continue;
-    c->smem[vn] = size_t(kMsThreads / 32) * 2 * 32 * c->cyc[vn]->np * sizeof(float);
+    c->smem[vn] = c->cyc[vn]->cta ? 0 : size_t(kMsThreads / 32) * 2 * 32 * c->cyc[vn]->np * sizeof(float);
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void *>(c->cyc[vn]->fn), kMsThreads,
-                                                  c->smem[vn]);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void *>(c->cyc[vn]->fn),
+                                                  c->cyc[vn]->threads, c->smem[vn]);
     c->grid_max[vn] = std::max(1, occ) * c->ctx->sm_count;
   }
 }
@@ -210,13 +210,13 @@ int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsP
   const int vn = (p->variant == CCGPU_SCMS1 || p->variant == CCGPU_SCMS2) ? VN_SC : (p->variant == CCGPU_NMS2D ? VN_2D : VN_PLAIN);
   if (p->variant != CCGPU_SPA && c->cyc[vn]) {
     const MsCyclicEntry *e = c->cyc[vn];
-    const uint64_t per_cta = uint64_t(kMsThreads / 32) * e->fpw;
+    const uint64_t per_cta = e->cta ? 1 : uint64_t(kMsThreads / 32) * e->fpw;
     const uint64_t want = (mp.frames + per_cta - 1) / per_cta;
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(want, c->grid_max[vn]));
     CU(cudaMemsetAsync(work, 0, sizeof(unsigned long long), stream));
     mp.work = work;
     void *args[] = { &mp };
-    CU(cudaLaunchKernel(reinterpret_cast<const void *>(e->fn), dim3(grid), dim3(kMsThreads), args, c->smem[vn], stream));
+    CU(cudaLaunchKernel(reinterpret_cast<const void *>(e->fn), dim3(grid), dim3(e->threads), args, c->smem[vn], stream));
     ctx->launches++;
     return CCGPU_OK;
   }

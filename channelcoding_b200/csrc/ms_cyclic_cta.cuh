@@ -1,0 +1,224 @@
+// ms_cyclic_cta.cuh -- K2c: the cyclic min-sum decoder of ms_cyclic.cuh for codes whose rows do not
+// fit one warp with register-resident messages (BCH(255,131): 124 rows of weight 68).
+//
+// Same arithmetic, same order, same outputs as ms_cyclic_kernel (reference codes/soft_decision.h:161-202);
+// the difference is the mapping: one CTA of WPF warps owns ONE frame, thread <-> parity-check row(s)
+// (row = tid + THREADS * i), the W messages of a row stay in registers, y[n] / S[n] / the decided
+// word (as 32-bit masks) live in shared memory, and the steps of the ordered column sum are
+// separated by __syncthreads instead of __syncwarp.  Several CTAs per SM hide the barrier latency.
+// CTAs are persistent and pull frames from the same global queue head.
+#pragma once
+#include <cfloat>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "channel.cuh"
+#include "ms_cyclic.cuh"
+#include "ms_params.h"
+#include "ms_shape.h"
+#include "ms_shape_cta.h"
+
+namespace ccgpu {
+
+template <class S, int VN>
+__global__ void __launch_bounds__(S::THREADS) ms_cyclic_cta_kernel(const __grid_constant__ MsParams p) {
+  constexpr int N = S::N, W = S::W, RPL = S::RPL, NPW = S::NPW, THREADS = S::THREADS, CPASS = S::CPASS;
+  constexpr bool WRAP = S::WRAP, SC = VN == VN_SC;
+  constexpr int NPAD = NPW * 32;
+  using T = typename S::taps;
+  __shared__ float ys[2 * NPAD];  // y[NPAD] then S[NPAD]: edge (row, tap) is yrow[tap] / yrow[NPAD + tap]
+  float *const ybuf = ys;
+  float *const sbuf = ys + NPAD;
+  __shared__ unsigned bword[CPASS * S::WPF];
+  __shared__ long long s_frame;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = S::K > 0 ? S::K : p.k;
+
+  int row[RPL];
+  bool rvalid[RPL];
+  float *yrow[RPL];
+  unsigned rmask[RPL][NPW];
+#pragma unroll
+  for (int i = 0; i < RPL; ++i) {
+    row[i] = tid + THREADS * i;
+    rvalid[i] = row[i] < k;
+    if (!rvalid[i]) row[i] = 0;
+    yrow[i] = ybuf + row[i];
+#pragma unroll
+    for (int w = 0; w < NPW; ++w) rmask[i][w] = 0;
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+      int c = row[i] + T::get(j);
+      if (WRAP && c >= N) c -= N;
+#pragma unroll
+      for (int w = 0; w < NPW; ++w)
+        if ((c >> 5) == w && rvalid[i]) rmask[i][w] |= 1u << (c & 31);
+    }
+  }
+
+  float r[RPL][W];
+  float qold[SC ? RPL : 1][SC ? W : 1];
+  unsigned long long cnt[6] = { 0, 0, 0, 0, 0, 0 };
+  long long frame = blockIdx.x;
+  constexpr int NBLK = (N + 3) >> 2;
+
+  while (frame < static_cast<long long>(p.frames)) {
+    // ---------------- frame source
+    if (p.src == SRC_HBM) {
+      for (int c = tid; c < N; c += THREADS) ybuf[c] = __ldg(p.y + frame * N + c);
+    } else if (p.src == SRC_PHILOX) {
+      for (int b = tid; b < NBLK; b += THREADS) {
+        const float4 v = awgn_block(p.seed, p.point, p.frame0 + static_cast<uint64_t>(frame), b, p.sigma);
+        const float vv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (4 * b + e < N) ybuf[4 * b + e] = vv[e];
+      }
+    } else if (tid == 0) {
+      unsigned long long rank = p.frame0 + static_cast<unsigned long long>(frame);
+      unsigned ones = p.flip_weight;
+      for (int c = 0; c < N; ++c) {
+        const unsigned long long zero_first = binom(N - c - 1, ones);
+        float v = 1.0f;
+        if (rank >= zero_first && ones > 0) {
+          rank -= zero_first;
+          --ones;
+          v = -1.0f;
+        }
+        ybuf[c] = v;
+      }
+    }
+    for (int c = tid; c < NPAD; c += THREADS) sbuf[c] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < RPL; ++i)
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        r[i][j] = 0.0f;
+        if (SC) qold[i][j] = 0.0f;
+      }
+    __syncthreads();
+
+    int it = 0;
+    bool stop = false;
+    for (;; ++it) {
+      // ============ VN + CN
+      float f1s[RPL], f2s[RPL], m1v[RPL];
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        float m1 = FLT_MAX, m2 = FLT_MAX;
+        unsigned par = 0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          int off = T::get(j);
+          if (WRAP && row[i] + off >= N) off -= N;
+          const float s = yrow[i][NPAD + off];
+          const float yy = yrow[i][off];
+          float e = __fsub_rn(s, r[i][j]);
+          if (VN == VN_2D) e = __fmul_rn(p.beta_f, e);
+          float q = __fadd_rn(e, yy);
+          if (SC) {
+            const float qo = qold[i][j];
+            if (p.variant == V_SCMS1) {
+              const bool keep = (qo == 0.0f) || ((qo > 0.0f) == (q > 0.0f) && (qo < 0.0f) == (q < 0.0f));
+              q = keep ? q : 0.0f;
+            } else {
+              q = (__fmul_rn(q, qo) > 0.0f) ? q : __fmul_rn(0.5f, __fadd_rn(q, qo));
+            }
+            qold[i][j] = q;
+          } else {
+            r[i][j] = q;
+          }
+          const float a = fabsf(q);
+          m2 = fminf(m2, fmaxf(m1, a));
+          m1 = fminf(m1, a);
+          par ^= __float_as_uint(q);
+        }
+        m1v[i] = m1;
+        f1s[i] = xor_sign(cn_magnitude(p, m1), par);
+        f2s[i] = xor_sign(cn_magnitude(p, m2), par);
+      }
+#pragma unroll
+      for (int i = 0; i < RPL; ++i)
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          const float q = SC ? qold[i][j] : r[i][j];
+          const float f = (fabsf(q) == m1v[i]) ? f2s[i] : f1s[i];
+          r[i][j] = xor_sign(f, __float_as_uint(q));
+        }
+      __syncthreads();
+      // ============ column sums, rows ascending
+      for (int c = tid; c < NPAD; c += THREADS) sbuf[c] = 0.0f;
+      __syncthreads();
+#pragma unroll
+      for (int pass = 0; pass < (WRAP ? 2 : 1); ++pass) {
+#pragma unroll
+        for (int j = W - 1; j >= 0; --j) {
+#pragma unroll
+          for (int i = 0; i < RPL; ++i) {
+            int off = T::get(j);
+            bool wrapped = false;
+            if (WRAP && row[i] + off >= N) {
+              off -= N;
+              wrapped = true;
+            }
+            if (rvalid[i] && wrapped == (pass == 1)) yrow[i][NPAD + off] = __fadd_rn(yrow[i][NPAD + off], r[i][j]);
+          }
+          __syncthreads();
+        }
+      }
+      // ============ totals, hard decision, stop test
+#pragma unroll
+      for (int cp = 0; cp < CPASS; ++cp) {
+        const int c = cp * THREADS + tid;
+        bool neg = false;
+        if (c < N) neg = __fadd_rn(sbuf[c], ybuf[c]) < 0.0f;
+        const unsigned bal = __ballot_sync(kFull, neg);
+        if (lane == 0) bword[cp * S::WPF + warp] = bal;
+      }
+      __syncthreads();
+      bool bad = false;
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        int ov = 0;
+#pragma unroll
+        for (int w = 0; w < NPW; ++w) ov += __popc(bword[w] & rmask[i][w]);
+        if (rvalid[i]) {
+          if (p.stop_rule == STOP_REF) bad |= (ov & 255) != 0;
+          else if (p.stop_rule == STOP_GF2) bad |= (ov & 1) != 0;
+          else bad = true;
+        }
+      }
+      stop = __syncthreads_or(bad) == 0;
+      if (stop || it + 1 >= p.max_iter) break;
+    }
+
+    // ---------------- outputs of this frame
+    const bool failed = !stop && p.stop_rule != STOP_NONE;
+    int nbits = 0;
+#pragma unroll
+    for (int w = 0; w < NPW; ++w) nbits += __popc(bword[w]);
+    if (p.bits)
+      for (int c = tid; c < N; c += THREADS) p.bits[frame * N + c] = static_cast<uint8_t>((bword[c >> 5] >> (c & 31)) & 1u);
+    if (p.L)
+      for (int c = tid; c < N; c += THREADS) p.L[frame * N + c] = __fadd_rn(sbuf[c], ybuf[c]);
+    if (tid == 0) {
+      if (p.iter) p.iter[frame] = static_cast<uint8_t>(failed ? p.max_iter : it);
+      if (p.failed) p.failed[frame] = failed ? 1 : 0;
+      cnt[C_FRAMES] += 1;
+      cnt[C_ITER] += static_cast<unsigned>(it + 1);
+      cnt[C_FAIL] += failed ? 1 : 0;
+      cnt[C_BIT_ERR] += static_cast<unsigned>(nbits);
+      cnt[C_FRAME_ERR] += (failed || nbits != 0) ? 1 : 0;
+      cnt[C_UNDETECTED] += (!failed && nbits != 0) ? 1 : 0;
+      s_frame = static_cast<long long>(gridDim.x) + static_cast<long long>(atomicAdd(p.work, 1ull));
+    }
+    __syncthreads();
+    frame = s_frame;
+    __syncthreads();
+  }
+  if (tid == 0 && p.counters != nullptr)
+    for (int s = 0; s < 6; ++s)
+      if (cnt[s]) atomicAdd(p.counters + s, cnt[s]);
+}
+
+}  // namespace ccgpu

@@ -48,6 +48,8 @@ enum : int { VN_PLAIN = 0 /* MS NMS OMS */, VN_SC = 1 /* SCMS1 SCMS2 */, VN_2D =
 struct MsCyclicEntry {
   const char *name;
   int n, k /* 0: rows at run time */, w, rpl, fpw, np, wrap, vn;
+  int threads;  // CTA size
+  int cta;      // 0: ms_cyclic_kernel (warp owns frames), 1: ms_cyclic_cta_kernel (CTA owns one frame)
   const int *taps;
   ms_kernel_fn fn;
 };

@@ -17,7 +17,7 @@ def test_reference_classes_drive_the_engine(tmp_path, kat):
     r = subprocess.run([BIN, str(tmp_path)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     lines = [l for l in r.stdout.splitlines() if l and not l.startswith("Using")]
-    table = [l for l in lines if l[:7].strip().isdigit()]
+    table = [l for l in lines if len(l.split()) == 2 and l.split()[0].isdigit()]  # "<errors> <wer>" log lines
     for w in range(4):  # Table 3 through the reference's own bitflip_simulation
         row = kat["bitflip_31_16_7"][str(w)]
         assert abs(float(table[w].split()[1]) - row["MS"] / row["patterns"]) < 1e-12
