@@ -643,43 +643,74 @@ int ccgpu_bitflip_point(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_p
   return counted_launch(ctx, code, params, mp, out);
 }
 
-int ccgpu_gf_decode(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8_t *words, uint64_t count,
-                    uint8_t *corrected, uint8_t *n_errors, uint8_t *failed) {
+int ccgpu_gf_decode_erasures(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8_t *words, uint64_t count,
+                             const uint8_t *erasure_pos, const uint8_t *erasure_cnt, uint32_t max_erasures,
+                             uint8_t *corrected, uint8_t *n_errors, uint8_t *failed) {
   if (!ctx || !code || !words || !corrected || !failed) return fail(ctx, CCGPU_ERR_INVALID, "null argument");
   if (code->ctx != ctx) return fail(ctx, CCGPU_ERR_INVALID, "code was not created on this context");
   if (code->spec.family == 2) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "algebraic decoding needs a BCH/RS code");
+  if ((erasure_pos == nullptr) != (erasure_cnt == nullptr)) return fail(ctx, CCGPU_ERR_INVALID, "erasure_pos and erasure_cnt go together");
+  if (erasure_pos && (max_erasures == 0 || max_erasures > 30)) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "max_erasures must be in 1..30");
   std::lock_guard<std::mutex> g(ctx->mu);
   if (count == 0) return CCGPU_OK;
   CU(cudaSetDevice(ctx->device));
   const size_t n = code->spec.n;
+  const size_t me = erasure_pos ? max_erasures : 0;
   const bool dev = is_device_ptr(words);
-  if (dev) {
-    if (!is_device_ptr(corrected) || !is_device_ptr(failed) || (n_errors && !is_device_ptr(n_errors)))
-      return fail(ctx, CCGPU_ERR_INVALID, "words is a device pointer: every output must be one too");
-    if (gf_launch(code->gf, words, count, corrected, n_errors, failed, ctx->sm_count, ctx->stream) != 0)
-      return cuda_fail(ctx, cudaGetLastError(), "gf_launch");
+  auto launch = [&](const uint8_t *w, uint64_t cnt, const uint8_t *ep, const uint8_t *ec, uint8_t *out, uint8_t *ne, uint8_t *fl,
+                    cudaStream_t st) -> int {
+    const int rc = gf_launch(code->gf, w, cnt, ep, ec, static_cast<int>(me), out, ne, fl, ctx->sm_count, st);
+    if (rc == -3) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "code not supported by the algebraic kernel (t <= 31, 2t <= 64, step = 1)");
+    if (rc != 0) return cuda_fail(ctx, cudaGetLastError(), "gf_launch");
     ctx->launches++;
     return CCGPU_OK;
+  };
+  if (dev) {
+    if (!is_device_ptr(corrected) || !is_device_ptr(failed) || (n_errors && !is_device_ptr(n_errors)) ||
+        (erasure_pos && (!is_device_ptr(erasure_pos) || !is_device_ptr(erasure_cnt))))
+      return fail(ctx, CCGPU_ERR_INVALID, "words is a device pointer: every other buffer must be one too");
+    return launch(words, count, erasure_pos, erasure_cnt, corrected, n_errors, failed, ctx->stream);
   }
-  const size_t per_word = 2 * n + 2;
-  const uint64_t chunk = std::min<uint64_t>(count, std::max<uint64_t>(1, (size_t(256) << 20) / per_word));
-  int rc = ensure_stage(ctx, chunk * per_word + 64);
+  // host buffers: chunks alternate between two slots so that copies and decoding overlap
+  const size_t per_word = 2 * n + 2 + me + (me ? 1 : 0);
+  const uint64_t chunk = std::max<uint64_t>(1024, std::min<uint64_t>((count + 7) / 8, (size_t(64) << 20) / per_word));
+  int rc = ensure_slots(ctx, chunk * per_word + 256);
   if (rc) return rc;
-  uint8_t *d_in = static_cast<uint8_t *>(ctx->d_stage);
-  uint8_t *d_out = d_in + chunk * n;
-  uint8_t *d_ne = d_out + chunk * n;
-  uint8_t *d_fail = d_ne + chunk;
-  for (uint64_t w0 = 0; w0 < count; w0 += chunk) {
+  CU(cudaEventRecord(ctx->main_ready, ctx->stream));
+  for (int s = 0; s < 2; ++s) CU(cudaStreamWaitEvent(ctx->slot_stream[s], ctx->main_ready, 0));
+  int slot = 0;
+  for (uint64_t w0 = 0; w0 < count; w0 += chunk, slot ^= 1) {
     const uint64_t nw = std::min(chunk, count - w0);
-    CU(cudaMemcpyAsync(d_in, words + w0 * n, nw * n, cudaMemcpyHostToDevice, ctx->stream));
-    if (gf_launch(code->gf, d_in, nw, d_out, d_ne, d_fail, ctx->sm_count, ctx->stream) != 0)
-      return cuda_fail(ctx, cudaGetLastError(), "gf_launch");
-    ctx->launches++;
-    CU(cudaMemcpyAsync(corrected + w0 * n, d_out, nw * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (n_errors) CU(cudaMemcpyAsync(n_errors + w0, d_ne, nw, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(failed + w0, d_fail, nw, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaStream_t st = ctx->slot_stream[slot];
+    uint8_t *d_in = static_cast<uint8_t *>(ctx->slot_buf[slot]);
+    uint8_t *d_out = d_in + chunk * n;
+    uint8_t *d_ne = d_out + chunk * n;
+    uint8_t *d_fail = d_ne + chunk;
+    uint8_t *d_ep = me ? d_fail + chunk : nullptr;
+    uint8_t *d_ec = me ? d_ep + chunk * me : nullptr;
+    CU(cudaMemcpyAsync(d_in, words + w0 * n, nw * n, cudaMemcpyHostToDevice, st));
+    if (me) {
+      CU(cudaMemcpyAsync(d_ep, erasure_pos + w0 * me, nw * me, cudaMemcpyHostToDevice, st));
+      CU(cudaMemcpyAsync(d_ec, erasure_cnt + w0, nw, cudaMemcpyHostToDevice, st));
+    }
+    rc = launch(d_in, nw, d_ep, d_ec, d_out, d_ne, d_fail, st);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(corrected + w0 * n, d_out, nw * n, cudaMemcpyDeviceToHost, st));
+    if (n_errors) CU(cudaMemcpyAsync(n_errors + w0, d_ne, nw, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(failed + w0, d_fail, nw, cudaMemcpyDeviceToHost, st));
   }
-  CU(cudaStreamSynchronize(ctx->stream));
+  for (int s = 0; s < 2; ++s) CU(cudaStreamSynchronize(ctx->slot_stream[s]));
+  return CCGPU_OK;
+}
+
+int ccgpu_gf_decode(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8_t *words, uint64_t count,
+                    uint8_t *corrected, uint8_t *n_errors, uint8_t *failed) {
+  return ccgpu_gf_decode_erasures(ctx, code, words, count, nullptr, nullptr, 0, corrected, n_errors, failed);
+}
+
+int ccgpu_code_set_recheck(ccgpu_code *code, int enable) {
+  if (!code) return CCGPU_ERR_INVALID;
+  code->gf.recheck = enable ? 1 : 0;
   return CCGPU_OK;
 }
 

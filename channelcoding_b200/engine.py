@@ -235,8 +235,12 @@ class Code:
                                                        C.addressof(c)))
         return c.as_dict()
 
-    def gf_decode(self, words, out=None):
-        """cyclic::correct_(.., hard_decision_tag) per word -> corrected, n_errors, failed"""
+    def set_recheck(self, enable):
+        _check(self.ctx, _lib.lib().ccgpu_code_set_recheck(self._h, int(bool(enable))))
+
+    def gf_decode(self, words, out=None, erasures=None):
+        """cyclic::correct_(.., hard_decision_tag) per word -> corrected, n_errors, failed.
+        erasures: optional (positions[count, max_e] uint8, counts[count] uint8)"""
         if _is_torch(words):
             import torch
             words = words.contiguous().view(-1, self.n)
@@ -250,8 +254,17 @@ class Code:
             if out is None:
                 out = (np.empty_like(words), np.empty(cnt, np.uint8), np.empty(cnt, np.uint8))
         corrected, nerr, failed = out
-        self.ctx._check(_lib.lib().ccgpu_gf_decode(self.ctx._h, self._h, _ptr(words), cnt, _ptr(corrected), _ptr(nerr),
-                                                   _ptr(failed)))
+        if erasures is None:
+            self.ctx._check(_lib.lib().ccgpu_gf_decode(self.ctx._h, self._h, _ptr(words), cnt, _ptr(corrected),
+                                                       _ptr(nerr), _ptr(failed)))
+        else:
+            epos, ecnt = erasures
+            if not _is_torch(epos):
+                epos = np.ascontiguousarray(epos, np.uint8).reshape(cnt, -1)
+                ecnt = np.ascontiguousarray(ecnt, np.uint8)
+            self.ctx._check(_lib.lib().ccgpu_gf_decode_erasures(self.ctx._h, self._h, _ptr(words), cnt, _ptr(epos),
+                                                                _ptr(ecnt), epos.shape[1], _ptr(corrected), _ptr(nerr),
+                                                                _ptr(failed)))
         return corrected, nerr, failed
 
 

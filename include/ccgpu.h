@@ -196,6 +196,21 @@ int ccgpu_bitflip_point(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_p
  *   failed    count      1 where the reference throws decoding_failure */
 int ccgpu_gf_decode(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8_t *words, uint64_t count,
                     uint8_t *corrected, uint8_t *n_errors, uint8_t *failed);
+/* the same with erasures -- the `erasures` argument of cyclic::correct (cyclic.h:331-344), folded into
+ * the locator as in hard_decision.h:127-131 / :171-172.  Word w has erasure_cnt[w] (<= max_erasures <= 30)
+ * erased positions erasure_pos[w * max_erasures + i]; e errors and f erasures are corrected when
+ * 2e + f <= 2t.  n_errors counts errors + erasures like cyclic.h:237.  Deviation: with an odd f the
+ * reference's Euklid stop rule (hard_decision.h:164: max = (2t + f) / 2, integer) also accepts locators one
+ * degree beyond that bound, where the solution is not unique; the engine reports failed = 1 there.
+ * For binary BCH the reference
+ * flips EVERY erased position (error values are all 1, bch.h:80-83) and relies on the re-syndrome
+ * check; the engine reproduces that. */
+int ccgpu_gf_decode_erasures(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8_t *words, uint64_t count,
+                             const uint8_t *erasure_pos, const uint8_t *erasure_cnt, uint32_t max_erasures,
+                             uint8_t *corrected, uint8_t *n_errors, uint8_t *failed);
+/* 1: always recompute the syndromes of the corrected word (cyclic.h:243-248).  Off by default: for
+ * erasure-free words the check is implied by "deg Lambda <= t and deg Lambda distinct roots" (DESIGN.md 4). */
+int ccgpu_code_set_recheck(ccgpu_code *code, int enable);
 
 #ifdef __cplusplus
 }

@@ -294,3 +294,99 @@ def test_wer_matches_reference_statistics(ctx, catalogue):
         p1, p2 = rw / rf, c["frame_errors"] / c["frames"]
         se = math.sqrt(p1 * (1 - p1) / rf + p2 * (1 - p2) / c["frames"])
         assert abs(p1 - p2) <= 1.96 * se + 1e-9, (eb, p1, p2, se)
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fam,q,t,count", [(1, 4, 3, 6000), (1, 8, 16, 3000), (1, 3, 2, 3000), (0, 5, 3, 3000),
+                                           (0, 6, 5, 2000)])
+def test_gf_decode_erasures_vs_oracle(ctx, fam, q, t, count):
+    """errors + erasures (cyclic::correct(b, erasures), hard_decision.h:171-172) against the Euklid
+    restatement word by word, decodable and undecodable mixes; binary codes follow the reference's
+    flip-every-erasure behaviour (bch.h:80-83)"""
+    rng = np.random.default_rng(q * 1000 + t)
+    oc = oracle.Code(fam, q, t)
+    code = ctx.bch(q, errors=t) if fam == 0 else ctx.rs(q, t)
+    n = oc.n
+    max_e = min(2 * t + 2, 30)
+    msgs = rng.integers(0, (1 << q) if fam == 1 else 2, size=(count, oc.l)).astype(np.uint8)
+    words = code.encode(msgs)
+    bad = words.copy()
+    epos = np.zeros((count, max_e), np.uint8)
+    ecnt = np.zeros(count, np.uint8)
+    for i in range(count):
+        f = int(rng.integers(0, max_e + 1))
+        e = int(rng.integers(0, max(1, (2 * t - f) // 2 + 2)))
+        e = min(e, n - f)
+        pos = rng.choice(n, f + e, replace=False)
+        if fam == 1:
+            bad[i, pos[:f]] = rng.integers(0, 1 << q, size=f).astype(np.uint8) * (rng.random() < 0.5)
+            bad[i, pos[f:]] ^= rng.integers(1, 1 << q, size=e).astype(np.uint8)
+        else:
+            bad[i, pos[:f]] = 0
+            bad[i, pos[f:]] ^= 1
+        epos[i, :f] = pos[:f]
+        ecnt[i] = f
+    out, nerr, failed = code.gf_decode(bad, erasures=(epos, ecnt))
+    sel = np.arange(min(count, 1500))
+    beyond = 0
+    for i in sel:
+        rho = int(ecnt[i])
+        oo, on, os_ = oc.hard_correct(bad[i:i + 1], [int(x) for x in epos[i, :rho]])
+        # bounded-distance region of errors-and-erasures decoding: 2 * errors + erasures <= 2t, i.e. the
+        # errata locator has degree L with 2L <= 2t + rho.  There the engine equals the reference exactly.
+        # With an ODD number of erasures the reference's Euklid stop rule (hard_decision.h:164,181:
+        # max = (2t + rho) / 2 in integer arithmetic) also accepts degree L = (2t + rho + 1) / 2, one beyond
+        # the guarantee, where the solution is not unique (it miscorrects in part of those cases); the
+        # engine declares a decoding failure there (documented deviation, DESIGN.md 7).
+        if os_[0] == 0 and 2 * int(on[0]) <= 2 * t + rho:
+            assert failed[i] == 0 and np.array_equal(out[i], oo[0]) and nerr[i] == on[0], (i, rho)
+        elif os_[0] == 0:
+            assert rho % 2 == 1 and 2 * int(on[0]) == 2 * t + rho + 1 and failed[i] == 1, (i, rho, on[0])
+            beyond += 1
+        else:
+            assert failed[i] == 1, (i, rho)
+        if failed[i] == 0:
+            assert os_[0] == 0
+    # every word constructed inside the bound is recovered
+    # erasure-only decoding up to 2t erasures recovers the word (RS); zero erasures == plain decode
+    out0, nerr0, failed0 = code.gf_decode(bad[ecnt == 0]) if (ecnt == 0).any() else (None, None, None)
+    if out0 is not None:
+        assert np.array_equal(out0, out[ecnt == 0]) and np.array_equal(failed0, failed[ecnt == 0])
+
+
+def test_exercises_with_erasures(ctx, kat, catalogue):
+    """exercises.c++ tasks 6.7 / 6.8: RS(7,3) with erasures"""
+    for key in ("6.7", "6.8"):
+        ex = kat["exercises"][key]
+        code = make_code(ctx, catalogue[ex["code"]])
+        er = np.zeros((1, 4), np.uint8)
+        er[0, :len(ex["erasures"])] = ex["erasures"]
+        out, nerr, failed = code.gf_decode(np.asarray([ex["received"]], np.uint8),
+                                           erasures=(er, np.asarray([len(ex["erasures"])], np.uint8)))
+        assert failed[0] == 0 and list(map(int, out[0])) == ex["expect"], key
+
+
+def test_gf_recheck_is_implied(ctx):
+    """the re-syndrome check of cyclic.h:243-248 never changes an erasure-free result (it is implied by
+    deg Lambda <= t with deg Lambda distinct roots): 2e5 RS(255,223) words with 0..24 errors, with and
+    without the check, and every accepted word has all-zero syndromes"""
+    rng = np.random.default_rng(77)
+    code = ctx.rs(8, 16)
+    oc = oracle.Code(1, 8, 16)
+    count = 200000
+    base = code.encode(rng.integers(0, 256, size=(512, code.l)).astype(np.uint8))
+    bad = np.tile(base, (count // 512 + 1, 1))[:count].copy()
+    ne = rng.integers(0, 25, size=count)
+    rows = np.repeat(np.arange(count), ne)
+    cols = rng.integers(0, 255, size=rows.size)
+    bad[rows, cols] ^= rng.integers(1, 256, size=rows.size).astype(np.uint8)
+    fast = code.gf_decode(bad)
+    code.set_recheck(True)
+    slow = code.gf_decode(bad)
+    code.set_recheck(False)
+    for a, b in zip(fast, slow):
+        assert np.array_equal(a, b)
+    ok = np.flatnonzero(fast[2] == 0)
+    assert 0.5 < len(ok) / count < 0.8
+    for i in ok[:: max(1, len(ok) // 400)]:
+        assert not oc.syndromes(fast[0][i]).any()

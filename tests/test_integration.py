@@ -22,4 +22,4 @@ def test_reference_classes_drive_the_engine(tmp_path, kat):
         row = kat["bitflip_31_16_7"][str(w)]
         assert abs(float(table[w].split()[1]) - row["MS"] / row["patterns"]) < 1e-12
     awgn = [l for l in lines if l.startswith("awgn")][0].split()
-    assert 0.05 < int(awgn[1]) / int(awgn[2]) < 0.5
+    assert 0.55 < int(awgn[1]) / int(awgn[2]) < 0.85  # sigma 0.75 is Eb/N0 = 1.9 dB for (63,36): WER about 0.7
