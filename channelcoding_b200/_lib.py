@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libccgpu.so")
+LIB_PATH = os.environ.get("CCGPU_LIB", os.path.join(_HERE, "libccgpu.so"))  # CCGPU_LIB: experimental builds
 
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_DEVICE = 0, -1, -2, -3, -4
 

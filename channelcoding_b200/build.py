@@ -14,11 +14,14 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(CSRC, "_obj")
-LIB = os.path.join(HERE, "libccgpu.so")
+OBJ = os.path.join(CSRC, "_obj" + ("_" + os.environ["CCGPU_VARIANT"] if os.environ.get("CCGPU_VARIANT") else ""))
+# CCGPU_VARIANT=<name> + CCGPU_EXTRA_FLAGS builds an experimental copy next to the product library
+VARIANT = os.environ.get("CCGPU_VARIANT", "")
+LIB = os.path.join(HERE, "libccgpu%s.so" % ("_" + VARIANT if VARIANT else ""))
 NVCC = os.environ.get("NVCC", "nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-Xptxas", "-v"]
+FLAGS += os.environ.get("CCGPU_EXTRA_FLAGS", "").split()
 
 
 def _groups():

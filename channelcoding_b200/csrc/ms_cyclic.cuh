@@ -37,12 +37,22 @@
 #include "ms_params.h"
 #include "ms_shape.h"
 
+#ifndef CCGPU_MS_YREG
+#define CCGPU_MS_YREG 0  /* measured: +18 registers cost more occupancy than the saved LDS gains (profiles/r1_notes.md) */
+#endif
+
 namespace ccgpu {
 
 constexpr unsigned kFull = 0xffffffffu;
 
 __device__ __forceinline__ float xor_sign(float v, unsigned signbits) {
   return __uint_as_float(__float_as_uint(v) ^ (signbits & 0x80000000u));
+}
+// value barrier: stops the compiler from re-associating an XOR that was folded once per row back
+// into the per-edge path
+__device__ __forceinline__ float opaque(float v) {
+  asm volatile("" : "+f"(v));
+  return v;
 }
 
 // fn_h of the variant applied to a non-negative minimum (soft_decision.h:204-213, :245-251)
@@ -66,6 +76,9 @@ template <class S, int VN>
 __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_constant__ MsParams p) {
   constexpr int N = S::N, W = S::W, RPL = S::RPL, NP = S::NP, FPW = S::FPW;
   constexpr bool WRAP = S::WRAP, SC = VN == VN_SC;
+  // y of the row's W edges is loop invariant: keep it in registers when the budget allows (saves one
+  // shared-memory load per edge and iteration)
+  constexpr bool YREG = CCGPU_MS_YREG && !SC && !WRAP && RPL * W <= 32;
   constexpr int ITEMS = FPW * N;            // columns handled by this warp, <= 32 * NP
   constexpr int SOFF = 32 * NP;             // S lives SOFF floats after y
   using T = typename S::taps;
@@ -150,6 +163,7 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
   int it = 0;
   float r[RPL][W];
   float qold[SC ? RPL : 1][SC ? W : 1];
+  float yreg[YREG ? RPL : 1][YREG ? W : 1];
   unsigned long long cnt_frames = 0, cnt_ferr = 0, cnt_berr = 0, cnt_iter = 0, cnt_fail = 0, cnt_und = 0;
   constexpr int NBLK = (N + 3) >> 2;
 
@@ -218,6 +232,12 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
         need_init = false;
       }
       __syncwarp();
+      if (YREG) {
+#pragma unroll
+        for (int i = 0; i < RPL; ++i)
+#pragma unroll
+          for (int j = 0; j < W; ++j) yreg[i][j] = yrow[i][T::get(j)];
+      }
     }
 
     // ============ VN + CN  (vertical__ / horizontal__)
@@ -231,7 +251,7 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
         int off = T::get(j);
         if (WRAP && row[i] + off >= N) off -= N;
         const float s = yrow[i][SOFF + off];
-        const float yy = yrow[i][off];
+        const float yy = YREG ? yreg[i][j] : yrow[i][off];
         float e = __fsub_rn(s, r[i][j]);                      // exclusive column sum (:135)
         if (VN == VN_2D) e = __fmul_rn(p.beta_f, e);          // normalised_vertical (:215-218)
         float q = __fadd_rn(e, yy);                           // unmodified_vertical (:205-209)
@@ -253,8 +273,8 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
         par ^= __float_as_uint(q);
       }
       m1v[i] = m1;
-      f1s[i] = xor_sign(cn_magnitude(p, m1), par);  // fold the row's sign parity in once
-      f2s[i] = xor_sign(cn_magnitude(p, m2), par);
+      f1s[i] = opaque(xor_sign(cn_magnitude(p, m1), par));  // fold the row's sign parity in once
+      f2s[i] = opaque(xor_sign(cn_magnitude(p, m2), par));
     }
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
