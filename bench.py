@@ -33,6 +33,17 @@ Q, T, ALPHA, MAX_ITER = 6, 5, 0.8, 50
 N, L_INFO, ROWS, W = 63, 36, 27, 18
 EDGES = ROWS * W
 ALGO_BYTES_PER_FRAME = 4 * N + 4 * ((N + 31) // 32) + 4  # LLR in, packed decisions + status out
+WORKLOAD = ("BCH(63,36) t=5 normalised min-sum alpha=0.8, <=50 iterations, early exit with the reference's stop rule, "
+            "AWGN Eb/N0=%g dB, all-zero codeword")
+
+
+def measured_traffic_per_frame():
+    """DRAM bytes per frame of the decode kernel from the committed ncu capture (profiles/)"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ms_cyclic_63_36.json")) as f:
+            return float(json.load(f)[0]["dram_bytes_per_frame"])
+    except Exception:
+        return None
 
 
 def measured_peaks():
@@ -140,8 +151,7 @@ def run_reference(args):
         "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BCH(63,36) t=5 NMS alpha=0.8, <=50 iterations, reference stop rule, AWGN Eb/N0=%g dB, "
-                               "all-zero codeword" % args.ebno, "ebno_db": args.ebno,
+        "config": {"workload": WORKLOAD % args.ebno, "ebno_db": args.ebno,
                    "frames_per_step": frames // max(1, args.steps)},
         "info_bits_per_s": value * L_INFO, "wer": werr / max(1, frames),
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind,
@@ -285,10 +295,10 @@ def main():
             "metric": "decoded frames/s, BCH(63,36) normalised min-sum", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "BCH(63,36) t=5 NMS alpha=0.8, <=50 iterations, reference stop rule, AWGN "
-                                   "Eb/N0=%g dB, all-zero codeword, %d frames per step per GPU resident in HBM "
-                                   "(%.2f GB of LLRs, larger than L2)" % (args.ebno, B, B * N * 4 / 1e9),
-                       "ebno_db": args.ebno, "frames_per_step_per_gpu": B, "l2": "inputs larger than L2",
+            "config": {"workload": WORKLOAD % args.ebno, "ebno_db": args.ebno, "frames_per_step_per_gpu": B,
+                       "resident_batch": "%d frames per step per GPU resident in HBM (%.2f GB of LLRs)"
+                                         % (B, B * N * 4 / 1e9),
+                       "l2": "inputs larger than L2",
                        "sharding": "frames split across ranks, no data-path collective"},
             "info_bits_per_s": value * L_INFO, "wer": wer, "avg_iterations": iters_exec,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": Be * N * 4,
@@ -301,8 +311,9 @@ def main():
                                           "all-reduce of 8 counters"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": which,
-                         "kernel": "ms_cyclic_kernel<W=18,RPL=1,NP=2,SC=0,WRAP=0>",
+                         "frac": achieved / hbm_peak,
+                         "traffic": (measured_traffic_per_frame() * B if measured_traffic_per_frame() else None),
+                         "peak_source": which, "kernel": "ms_cyclic_kernel<Shape<63,27,...>, VN_PLAIN>",
                          "bytes_per_frame": ALGO_BYTES_PER_FRAME,
                          "note": "the decoder is on-chip ALU/shared-memory bound, not HBM bound: see alu"},
             "alu": {"model": "avg_iters*(11E+2n) lane-ops/frame (SURVEY 8d)", "lane_ops_per_frame": lane_ops,
