@@ -48,9 +48,10 @@ struct ccgpu_code {
   CodeSpec spec;
   HShape shape;
   // min-sum kernel selection per vertical-node flavour (VN_PLAIN, VN_SC, VN_2D)
-  const MsCyclicEntry *cyc[3] = { nullptr, nullptr, nullptr };
-  int grid_max[3] = { 0, 0, 0 };
-  size_t smem[3] = { 0, 0, 0 };
+  const MsCyclicEntry *cyc[VN_COUNT] = {};
+  int grid_max[VN_COUNT] = {};
+  size_t smem[VN_COUNT] = {};
+  bool all_columns_covered = false;
   MsCsrDevice csr;     // general-H kernel tables (device)
   GfDevice gf;         // algebraic decoder tables (device)
 };
@@ -140,11 +141,20 @@ __global__ void __launch_bounds__(kAwgnThreads) awgn_llr_kernel(float *__restric
   }
 }
 
+bool columns_covered(const CodeSpec &s) {
+  for (unsigned c = 0; c < s.n; ++c) {
+    bool any = false;
+    for (unsigned r = 0; r < s.rows && !any; ++r) any = s.H[size_t(r) * s.n + c] != 0;
+    if (!any) return false;
+  }
+  return true;
+}
+
 // pick the cyclic kernel instantiations (one per vertical-node flavour) compiled for exactly this
 // H: same n, same tap offsets, and either the same number of rows without wrap-around or a
 // redundant (run-time rows, wrap-around) shape.  Nothing fits -> CSR kernel.
 void select_cyclic(ccgpu_code *c) {
-  for (int vn = 0; vn < 3; ++vn) c->cyc[vn] = nullptr;
+  for (int vn = 0; vn < VN_COUNT; ++vn) c->cyc[vn] = nullptr;
   if (c->shape.kind > 1 || c->shape.taps.empty()) return;
   const int n = static_cast<int>(c->spec.n), k = static_cast<int>(c->spec.rows);
   const int w = static_cast<int>(c->shape.taps.size());
@@ -157,7 +167,7 @@ void select_cyclic(ccgpu_code *c) {
     if (c->cyc[e->vn] && !exact) continue;  // an exact shape wins over the redundant one
     c->cyc[e->vn] = e;
   }
-  for (int vn = 0; vn < 3; ++vn) {
+  for (int vn = 0; vn < VN_COUNT; ++vn) {
     if (!c->cyc[vn]) continue;
     c->smem[vn] = c->cyc[vn]->cta ? 0 : size_t(kMsThreads / 32) * 2 * 32 * c->cyc[vn]->np * sizeof(float);
     int occ = 0;
@@ -170,6 +180,7 @@ void select_cyclic(ccgpu_code *c) {
 int finish_code(ccgpu_ctx *ctx, ccgpu_code *c) {
   c->ctx = ctx;
   c->shape = analyse_H(c->spec.H.data(), c->spec.rows, c->spec.n);
+  c->all_columns_covered = columns_covered(c->spec);
   if (!ctx) return CCGPU_OK;  // host-only description: no device tables, no decoding
   select_cyclic(c);
   int rc = ms_csr_upload(c->spec.H.data(), c->spec.rows, c->spec.n, &c->csr);
@@ -200,6 +211,9 @@ void fill_decoder(MsParams &mp, const ccgpu_code *c, const ccgpu_ms_params *p) {
   mp.alpha_f = static_cast<float>(p->alpha);  // double -> float where the reference's functor call does
   mp.beta_f = static_cast<float>(p->beta);
   mp.beta_d = p->beta;
+  // the reference's stop test passes iff every row's integer overlap with b is 0 mod 256; when every
+  // column is covered by some row and all row weights are < 256 that is exactly "b is all-zero"
+  mp.stop_simple = (p->stop_rule == CCGPU_STOP_REF_ZERO_OVERLAP && c->all_columns_covered && c->shape.max_row_weight < 256) ? 1 : 0;
 }
 
 // launch the min-sum decoder for one batch described by mp (source/outputs already filled)
@@ -207,8 +221,11 @@ int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsP
   if (mp.frames == 0) return CCGPU_OK;
   cudaStream_t stream = slot < 0 ? ctx->stream : ctx->slot_stream[slot];
   unsigned long long *work = ctx->d_work + (slot + 1);
-  const int vn = (p->variant == CCGPU_SCMS1 || p->variant == CCGPU_SCMS2) ? VN_SC : (p->variant == CCGPU_NMS2D ? VN_2D : VN_PLAIN);
-  if (p->variant != CCGPU_SPA && c->cyc[vn]) {
+  const int vn = (p->variant == CCGPU_SCMS1 || p->variant == CCGPU_SCMS2) ? VN_SC
+                 : p->variant == CCGPU_NMS2D                             ? VN_2D
+                 : p->variant == CCGPU_SPA                               ? VN_SPA
+                                                                         : VN_PLAIN;
+  if (c->cyc[vn]) {
     const MsCyclicEntry *e = c->cyc[vn];
     const uint64_t per_cta = e->cta ? 1 : uint64_t(kMsThreads / 32) * e->fpw;
     const uint64_t want = (mp.frames + per_cta - 1) / per_cta;
@@ -364,6 +381,7 @@ int ccgpu_code_set_rows(ccgpu_code *code, uint32_t rows) {
     return fail(ctx, CCGPU_ERR_INVALID, e.what());
   }
   code->shape = analyse_H(code->spec.H.data(), code->spec.rows, code->spec.n);
+  code->all_columns_covered = columns_covered(code->spec);
   if (!ctx) return CCGPU_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);

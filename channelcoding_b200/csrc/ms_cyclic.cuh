@@ -75,7 +75,7 @@ __device__ __forceinline__ unsigned long long binom(unsigned n, unsigned r) {
 template <class S, int VN>
 __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_constant__ MsParams p) {
   constexpr int N = S::N, W = S::W, RPL = S::RPL, NP = S::NP, FPW = S::FPW;
-  constexpr bool WRAP = S::WRAP, SC = VN == VN_SC;
+  constexpr bool WRAP = S::WRAP, SC = VN == VN_SC, SPA = VN == VN_SPA;
   // y of the row's W edges is loop invariant: keep it in registers when the budget allows (saves one
   // shared-memory load per edge and iteration)
   constexpr bool YREG = CCGPU_MS_YREG && !SC && !WRAP && RPL * W <= 32;
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
   bool need_init = true;
   int it = 0;
   float r[RPL][W];
-  float qold[SC ? RPL : 1][SC ? W : 1];
+  float qold[(SC || SPA) ? RPL : 1][(SC || SPA) ? W : 1];  // previous q (SCMS) / prefix products (SPA)
   float yreg[YREG ? RPL : 1][YREG ? W : 1];
   unsigned long long cnt_frames = 0, cnt_ferr = 0, cnt_berr = 0, cnt_iter = 0, cnt_fail = 0, cnt_und = 0;
   constexpr int NBLK = (N + 3) >> 2;
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
 #pragma unroll
           for (int j = 0; j < W; ++j) {
             r[i][j] = 0.0f;
-            if (SC) qold[i][j] = 0.0f;
+            if (SC || SPA) qold[i][j] = 0.0f;
           }
         it = 0;
         need_init = false;
@@ -241,6 +241,33 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
     }
 
     // ============ VN + CN  (vertical__ / horizontal__)
+    if (SPA) {
+      // extension (not in the reference): sum-product / tanh rule.  r_j = 2 atanh( prod_{i != j} tanh(q_i / 2) ),
+      // the exclusive product as prefix * suffix, clamped like oracle/ms_oracle.c so that atanh stays finite
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        float prod = 1.0f;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+          int off = T::get(j);
+          if (WRAP && row[i] + off >= N) off -= N;
+          const float q = __fadd_rn(__fsub_rn(yrow[i][SOFF + off], r[i][j]), yrow[i][off]);
+          const float th = tanhf(0.5f * q);
+          qold[i][j] = prod;  // product of the taps before j
+          prod *= th;
+          r[i][j] = th;
+        }
+        float suffix = 1.0f;  // product of the taps after j
+#pragma unroll
+        for (int j = W - 1; j >= 0; --j) {
+          const float th = r[i][j];
+          float pr = qold[i][j] * suffix;
+          pr = fminf(fmaxf(pr, -0.99999994f), 0.99999994f);
+          r[i][j] = 2.0f * atanhf(pr);
+          suffix *= th;
+        }
+      }
+    } else {
     float f1s[RPL], f2s[RPL], m1v[RPL];
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
@@ -286,6 +313,7 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
         r[i][j] = xor_sign(f, __float_as_uint(q));  // sign = prod of the other signs (:114,:118)
       }
     }
+    }
     __syncwarp();
 
     // ============ column sums, rows ascending (column_sum :86-98)
@@ -319,20 +347,30 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
       if (cvalid[ps]) neg = __fadd_rn(sbuf[lane + 32 * ps], ybuf[lane + 32 * ps]) < 0.0f;
       bw[ps] = __ballot_sync(kFull, neg);
     }
-    bool bad = false;
+    bool stop;
+    if (p.stop_simple) {
+      // reference rule on a matrix whose rows cover every column with weight < 256: every overlap is
+      // zero exactly when the decided word is all-zero (host sets the flag, see api.cu fill_decoder)
+      unsigned anyone = 0;
 #pragma unroll
-    for (int i = 0; i < RPL; ++i) {
-      int ov = 0;
+      for (int ps = 0; ps < NP; ++ps) anyone |= bw[ps] & cmask[ps];
+      stop = anyone == 0u;
+    } else {
+      bool bad = false;
 #pragma unroll
-      for (int ps = 0; ps < NP; ++ps) ov += __popc(bw[ps] & rmask[i][ps]);
-      if (rvalid[i]) {
-        if (p.stop_rule == STOP_REF) bad |= (ov & 255) != 0;
-        else if (p.stop_rule == STOP_GF2) bad |= (ov & 1) != 0;
-        else bad = true;
+      for (int i = 0; i < RPL; ++i) {
+        int ov = 0;
+#pragma unroll
+        for (int ps = 0; ps < NP; ++ps) ov += __popc(bw[ps] & rmask[i][ps]);
+        if (rvalid[i]) {
+          if (p.stop_rule == STOP_REF) bad |= (ov & 255) != 0;
+          else if (p.stop_rule == STOP_GF2) bad |= (ov & 1) != 0;
+          else bad = true;
+        }
       }
+      const unsigned badm = __ballot_sync(kFull, bad);
+      stop = (badm & gmask) == 0u;
     }
-    const unsigned badm = __ballot_sync(kFull, bad);
-    const bool stop = (badm & gmask) == 0u;
     const bool last = it + 1 >= p.max_iter;
     const bool fin = active && (stop || last);
     const unsigned finm = __ballot_sync(kFull, fin);

@@ -18,6 +18,7 @@ struct MsParams {
   int32_t n, k;
   // ---- decoder
   int32_t variant, stop_rule, max_iter, src;
+  int32_t stop_simple, pad1;  // 1: STOP_REF on an H where it is equivalent to "decided word is all-zero"
   float alpha_f, beta_f;  // alpha / beta converted double -> float exactly where the reference does
   double beta_d;          // OMS works in double (soft_decision.h:245-251)
   // ---- frame source
@@ -43,7 +44,7 @@ enum : int { C_FRAMES = 0, C_FRAME_ERR = 1, C_BIT_ERR = 2, C_ITER = 3, C_FAIL = 
 using ms_kernel_fn = void (*)(MsParams);
 
 // vertical-node flavour a kernel is compiled for
-enum : int { VN_PLAIN = 0 /* MS NMS OMS */, VN_SC = 1 /* SCMS1 SCMS2 */, VN_2D = 2 /* 2DNMS */ };
+enum : int { VN_PLAIN = 0 /* MS NMS OMS */, VN_SC = 1 /* SCMS1 SCMS2 */, VN_2D = 2 /* 2DNMS */, VN_SPA = 3 /* sum-product */, VN_COUNT = 4 };
 
 struct MsCyclicEntry {
   const char *name;

@@ -156,6 +156,23 @@ def test_sum_product_extension(ctx, catalogue):
     assert (gb[same] == ob[same]).all(axis=1).mean() >= 0.995
     rel = np.abs(gL[same] - oL[same]) / np.maximum(1.0, np.abs(oL[same]))
     assert np.median(rel) < 1e-5 and np.quantile(rel, 0.99) < 1e-3
+    # the same on the general (CSR) kernel: rows permuted so that the cyclic structure is gone
+    perm = np.random.default_rng(2).permutation(code.h_rows)
+    g = ctx.from_dense(code.H()[perm], e["rate"])
+    assert code.kernel == 1 and g.kernel == 2
+    gb2, gL2, gi2, gf2 = g.decode(llr, "SPA", max_iter=10, stop_rule=1)
+    ob2, oL2, oi2, of2 = oracle.min_sum(code.H()[perm], llr, "SPA", max_iter=10, stop_rule=1)
+    same2 = (gi2 == oi2) & (gf2 == of2)
+    assert same2.mean() >= 0.995 and (gb2[same2] == ob2[same2]).all(axis=1).mean() >= 0.995
+    # larger code on the cyclic kernel
+    e63 = catalogue["bch_63_36"]
+    c63 = make_code(ctx, e63)
+    sig = oracle.sigma(e63["rate"], 4.0)
+    y = (2.0 / sig ** 2 * (1 + sig * rng.standard_normal((300, 63)))).astype(np.float32)
+    gb, gL, gi, gf = c63.decode(y, "SPA", max_iter=20, stop_rule=1)
+    ob, oL, oi, of = oracle.min_sum(c63.H(), y, "SPA", max_iter=20, stop_rule=1)
+    same = (gi == oi) & (gf == of)
+    assert same.mean() >= 0.97 and (gb[same] == ob[same]).all(axis=1).mean() >= 0.99
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -390,3 +407,18 @@ def test_gf_recheck_is_implied(ctx):
     assert 0.5 < len(ok) / count < 0.8
     for i in ok[:: max(1, len(ok) // 400)]:
         assert not oc.syndromes(fast[0][i]).any()
+
+
+def test_uncovered_columns_use_the_general_stop_test(ctx, catalogue, golden_codes):
+    """a matrix whose rows do not cover every column: the reference's stop rule is then NOT equivalent to
+    'decided word is all-zero' (bits in uncovered columns are ignored), the kernel must evaluate overlaps"""
+    H = golden_H(golden_codes, catalogue, "bch_63_36")[:10]
+    code = ctx.from_dense(H, 36 / 63)
+    assert code.kernel == 1 and code.h_rows == 10
+    rng = np.random.default_rng(12)
+    y = (1 + 0.6 * rng.standard_normal((500, 63))).astype(np.float32)
+    y[:, 50:] = -np.abs(y[:, 50:])  # uncovered columns decided as ones
+    for stop in (0, 1):
+        assert_same(code.decode(y, "NMS", 0.8, 0.0, 20, stop), oracle.min_sum(H, y, "NMS", 0.8, 0.0, 20, stop), "partial H")
+    gb, gL, gi, gf = code.decode(y, "NMS", 0.8, 0.0, 20, 0)
+    assert (gf == 0).any() and gb[gf == 0][:, 50:].all()
