@@ -170,7 +170,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--ebno", type=float, default=4.0)
     ap.add_argument("--frames", type=int, default=1 << 22, help="frames per step per GPU (resident batch)")
-    ap.add_argument("--e2e-frames", type=int, default=1 << 20, help="frames per step per GPU for the host-buffer path")
+    ap.add_argument("--e2e-frames", type=int, default=1 << 22, help="frames per step per GPU for the host-buffer path")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

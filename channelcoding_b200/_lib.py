@@ -70,6 +70,7 @@ def lib():
     L.ccgpu_code_to_string.argtypes = [vp, C.c_char_p, C.c_char_p, C.c_size_t]
     L.ccgpu_code_H.argtypes = [vp, u8p]
     L.ccgpu_code_poly.argtypes = [vp, i32, vp, C.c_size_t]
+    L.ccgpu_code_H_alt.argtypes = [vp, i32, vp, C.POINTER(u32)]
     L.ccgpu_gf_tables.argtypes = [u32, u32, vp, vp]
     L.ccgpu_encode.argtypes = [vp, u8p, u64, u8p]
     L.ccgpu_decode_llr.argtypes = [vp, vp, C.POINTER(MsParams), vp, u64, vp, vp, vp, vp]
@@ -97,6 +98,6 @@ def lib():
 EXPORTS = ["ccgpu_abi_version", "ccgpu_create", "ccgpu_destroy", "ccgpu_last_error", "ccgpu_set_stream",
            "ccgpu_get_stream", "ccgpu_sync", "ccgpu_kernel_launches", "ccgpu_bch_create", "ccgpu_rs_create",
            "ccgpu_code_from_dense", "ccgpu_code_set_rows", "ccgpu_code_destroy", "ccgpu_code_get_info",
-           "ccgpu_code_to_string", "ccgpu_code_H", "ccgpu_code_poly", "ccgpu_gf_tables", "ccgpu_encode",
+           "ccgpu_code_to_string", "ccgpu_code_H", "ccgpu_code_H_alt", "ccgpu_code_poly", "ccgpu_gf_tables", "ccgpu_encode",
            "ccgpu_decode_llr", "ccgpu_sigma", "ccgpu_shannon_limit_db", "ccgpu_sweep_start_ebno", "ccgpu_sweep_samples", "ccgpu_awgn_llr", "ccgpu_awgn_point", "ccgpu_bitflip_point",
            "ccgpu_gf_decode", "ccgpu_gf_decode_erasures", "ccgpu_code_set_recheck"]

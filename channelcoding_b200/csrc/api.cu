@@ -18,6 +18,9 @@
 
 using namespace ccgpu;
 
+// host-buffer calls are pipelined over this many staging slots (stream + device buffer each)
+constexpr int kSlots = 3;
+
 // ------------------------------------------------------------------------------------------------
 struct ccgpu_ctx {
   int device = 0;
@@ -33,13 +36,13 @@ struct ccgpu_ctx {
   unsigned long long *d_counters = nullptr;
   unsigned long long *d_work = nullptr;  // queue heads of the dynamically scheduled kernels: [0] main, [1..2] slots
   ccgpu_counters *h_counters = nullptr;  // pinned
-  // host-buffer calls are cut into chunks that alternate between two slots (stream + staging
+  // host-buffer calls are cut into chunks that rotate over kSlots slots (stream + staging
   // buffer each), so the H2D copy of chunk i+1 and the D2H copy of chunk i-1 overlap the decode
   // of chunk i
-  cudaStream_t slot_stream[2] = { nullptr, nullptr };
-  cudaEvent_t slot_done[2] = { nullptr, nullptr };
+  cudaStream_t slot_stream[kSlots] = {};
+  cudaEvent_t slot_done[kSlots] = {};
   cudaEvent_t main_ready = nullptr;
-  void *slot_buf[2] = { nullptr, nullptr };
+  void *slot_buf[kSlots] = {};
   size_t slot_bytes = 0;
 };
 
@@ -82,18 +85,18 @@ bool is_device_ptr(const void *p) {
 }
 
 int ensure_slots(ccgpu_ctx *ctx, size_t bytes) {
-  for (int s = 0; s < 2; ++s) {
+  for (int s = 0; s < kSlots; ++s) {
     if (!ctx->slot_stream[s]) CU(cudaStreamCreateWithFlags(&ctx->slot_stream[s], cudaStreamNonBlocking));
     if (!ctx->slot_done[s]) CU(cudaEventCreateWithFlags(&ctx->slot_done[s], cudaEventDisableTiming));
   }
   if (!ctx->main_ready) CU(cudaEventCreateWithFlags(&ctx->main_ready, cudaEventDisableTiming));
   if (bytes <= ctx->slot_bytes) return CCGPU_OK;
-  for (int s = 0; s < 2; ++s) {
+  for (int s = 0; s < kSlots; ++s) {
     if (ctx->slot_buf[s]) cudaFree(ctx->slot_buf[s]);
     ctx->slot_buf[s] = nullptr;
   }
   ctx->slot_bytes = 0;
-  for (int s = 0; s < 2; ++s) CU(cudaMalloc(&ctx->slot_buf[s], bytes));
+  for (int s = 0; s < kSlots; ++s) CU(cudaMalloc(&ctx->slot_buf[s], bytes));
   ctx->slot_bytes = bytes;
   return CCGPU_OK;
 }
@@ -264,7 +267,7 @@ int ccgpu_create(int device, ccgpu_ctx **out) {
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
       cudaMalloc(&ctx->d_counters, sizeof(ccgpu_counters)) != cudaSuccess ||
-      cudaMalloc(&ctx->d_work, 3 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_work, (kSlots + 1) * sizeof(unsigned long long)) != cudaSuccess ||
       cudaMallocHost(&ctx->h_counters, sizeof(ccgpu_counters)) != cudaSuccess) {
     cudaGetLastError();
     delete ctx;
@@ -281,7 +284,7 @@ void ccgpu_destroy(ccgpu_ctx *ctx) {
   if (ctx->d_stage) cudaFree(ctx->d_stage);
   if (ctx->d_counters) cudaFree(ctx->d_counters);
   if (ctx->d_work) cudaFree(ctx->d_work);
-  for (int s = 0; s < 2; ++s) {
+  for (int s = 0; s < kSlots; ++s) {
     if (ctx->slot_stream[s]) {
       cudaStreamSynchronize(ctx->slot_stream[s]);
       cudaStreamDestroy(ctx->slot_stream[s]);
@@ -436,6 +439,15 @@ int ccgpu_code_H(const ccgpu_code *code, uint8_t *out) {
   return CCGPU_OK;
 }
 
+int ccgpu_code_H_alt(const ccgpu_code *code, int as_reference, uint8_t *out, uint32_t *rows) {
+  if (!code || !rows || code->spec.family == 2) return CCGPU_ERR_INVALID;
+  unsigned r = 0;
+  const std::vector<uint8_t> M = code->spec.h_alt(as_reference != 0, &r);
+  *rows = r;
+  if (out) std::memcpy(out, M.data(), M.size());
+  return CCGPU_OK;
+}
+
 int ccgpu_code_poly(const ccgpu_code *code, int which, uint16_t *out, size_t cap) {
   if (!code || !out) return CCGPU_ERR_INVALID;
   const Poly &p = which ? code->spec.h : code->spec.g;
@@ -536,13 +548,13 @@ int ccgpu_decode_llr(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_para
   }
   // host buffers: chunks alternate between two slots so that copies and decoding overlap
   const size_t per_frame = n * sizeof(float) + n + (L ? n * sizeof(float) : 0) + 2;
-  const uint64_t chunk = std::max<uint64_t>(1024, std::min<uint64_t>((frames + 7) / 8, (size_t(64) << 20) / per_frame));
+  const uint64_t chunk = std::max<uint64_t>(1024, std::min<uint64_t>((frames + 15) / 16, (size_t(32) << 20) / per_frame));
   rc = ensure_slots(ctx, chunk * per_frame + 256);
   if (rc) return rc;
   CU(cudaEventRecord(ctx->main_ready, ctx->stream));
-  for (int s = 0; s < 2; ++s) CU(cudaStreamWaitEvent(ctx->slot_stream[s], ctx->main_ready, 0));
+  for (int s = 0; s < kSlots; ++s) CU(cudaStreamWaitEvent(ctx->slot_stream[s], ctx->main_ready, 0));
   int slot = 0;
-  for (uint64_t f0 = 0; f0 < frames; f0 += chunk, slot ^= 1) {
+  for (uint64_t f0 = 0; f0 < frames; f0 += chunk, slot = (slot + 1) % kSlots) {
     const uint64_t nf = std::min(chunk, frames - f0);
     cudaStream_t st = ctx->slot_stream[slot];
     char *base = static_cast<char *>(ctx->slot_buf[slot]);
@@ -565,7 +577,7 @@ int ccgpu_decode_llr(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_para
     if (iter) CU(cudaMemcpyAsync(iter + f0, d_iter, nf, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(failed + f0, d_failed, nf, cudaMemcpyDeviceToHost, st));
   }
-  for (int s = 0; s < 2; ++s) CU(cudaStreamSynchronize(ctx->slot_stream[s]));
+  for (int s = 0; s < kSlots; ++s) CU(cudaStreamSynchronize(ctx->slot_stream[s]));
   return CCGPU_OK;
 }
 
@@ -691,13 +703,13 @@ int ccgpu_gf_decode_erasures(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8
   }
   // host buffers: chunks alternate between two slots so that copies and decoding overlap
   const size_t per_word = 2 * n + 2 + me + (me ? 1 : 0);
-  const uint64_t chunk = std::max<uint64_t>(1024, std::min<uint64_t>((count + 7) / 8, (size_t(64) << 20) / per_word));
+  const uint64_t chunk = std::max<uint64_t>(1024, std::min<uint64_t>((count + 15) / 16, (size_t(32) << 20) / per_word));
   int rc = ensure_slots(ctx, chunk * per_word + 256);
   if (rc) return rc;
   CU(cudaEventRecord(ctx->main_ready, ctx->stream));
-  for (int s = 0; s < 2; ++s) CU(cudaStreamWaitEvent(ctx->slot_stream[s], ctx->main_ready, 0));
+  for (int s = 0; s < kSlots; ++s) CU(cudaStreamWaitEvent(ctx->slot_stream[s], ctx->main_ready, 0));
   int slot = 0;
-  for (uint64_t w0 = 0; w0 < count; w0 += chunk, slot ^= 1) {
+  for (uint64_t w0 = 0; w0 < count; w0 += chunk, slot = (slot + 1) % kSlots) {
     const uint64_t nw = std::min(chunk, count - w0);
     cudaStream_t st = ctx->slot_stream[slot];
     uint8_t *d_in = static_cast<uint8_t *>(ctx->slot_buf[slot]);
@@ -717,7 +729,7 @@ int ccgpu_gf_decode_erasures(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8
     if (n_errors) CU(cudaMemcpyAsync(n_errors + w0, d_ne, nw, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(failed + w0, d_fail, nw, cudaMemcpyDeviceToHost, st));
   }
-  for (int s = 0; s < 2; ++s) CU(cudaStreamSynchronize(ctx->slot_stream[s]));
+  for (int s = 0; s < kSlots; ++s) CU(cudaStreamSynchronize(ctx->slot_stream[s]));
   return CCGPU_OK;
 }
 

@@ -135,6 +135,22 @@ struct CodeSpec {
     for (unsigned rr = 1; rr < rows; ++rr)
       for (unsigned c = 0; c < n; ++c) H[rr * n + (c + 1) % n] = H[(rr - 1) * n + c];
   }
+  // "H from the roots of g(x)" -- cyclic::H_alt<T>() of codes/cyclic.h:361-385: row block i (i < t) holds the
+  // binary expansion (q rows, least significant bit first) of alpha^(col * (2i + 1)).  as_reference = true
+  // reproduces the reference's from_power (exponent reduced mod 2^q instead of mod n, galois.h:182-184,
+  // SURVEY C4), which yields an invalid matrix for exponents >= 2^q; false reduces mod n.
+  std::vector<uint8_t> h_alt(bool as_reference, unsigned *rows_out) const {
+    if (family == 2) throw std::invalid_argument("h_alt needs a BCH/RS code");
+    std::vector<uint8_t> M(static_cast<size_t>(t) * q * n, 0);
+    for (unsigned i = 0; i < t; ++i)
+      for (unsigned c = 0; c < n; ++c) {
+        const unsigned power = c * (2 * i + 1);
+        const unsigned v = as_reference ? F.exp[power % F.size] : F.exp[power % n];
+        for (unsigned b = 0; b < q; ++b) M[(static_cast<size_t>(i) * q + b) * n + c] = (v >> b) & 1u;
+      }
+    *rows_out = t * q;
+    return M;
+  }
   std::string to_string(const std::string &tag) const {
     return "(" + std::to_string(n) + ", " + std::to_string(l) + ", " + std::to_string(dmin) + ")-" + tag;
   }

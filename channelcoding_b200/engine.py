@@ -165,6 +165,14 @@ class Code:
         _check(self.ctx, _lib.lib().ccgpu_code_H(self._h, out.ctypes.data))
         return out
 
+    def H_alt(self, as_reference=False):
+        """cyclic::H_alt<T>() (cyclic.h:361-385); as_reference reproduces the reference's exponent bug"""
+        rows = C.c_uint32()
+        _check(self.ctx, _lib.lib().ccgpu_code_H_alt(self._h, int(as_reference), None, C.byref(rows)))
+        out = np.zeros((rows.value, self.n), np.uint8)
+        _check(self.ctx, _lib.lib().ccgpu_code_H_alt(self._h, int(as_reference), out.ctypes.data, C.byref(rows)))
+        return out
+
     def poly(self, which):
         out = np.zeros(1024, np.uint16)
         m = _lib.lib().ccgpu_code_poly(self._h, {"g": 0, "h": 1}[which], out.ctypes.data, 1024)

@@ -238,6 +238,26 @@ public:
     return r;
   }
 
+  // ---- correct(b, erasures) of cyclic.h:331-344.  Soft tags: the channel value of every erased position is
+  // set to 0 before decoding (cyclic.h:261-262).  Hard tags: errors-and-erasures decoding
+  // (hard_decision.h:127-131 / :171-172) -- at most 30 erasures per word.
+  template <typename Return_type = uint8_t, typename InputSequence>
+  std::vector<Return_type> correct(const InputSequence &b, const std::vector<unsigned> &erasures) const {
+    if (erasures.empty()) return correct<Return_type>(b);
+    const unsigned n = h_->info.n;
+    if (b.size() != n)
+      throw std::runtime_error("Channel code word has the wrong size (" + std::to_string(b.size()) + "). Expected " +
+                               std::to_string(n));
+    std::vector<uint8_t> out(n);
+    uint8_t failed = 0;
+    correct_erased(b, erasures, out.data(), &failed, std::is_base_of<soft_decision_tag, Algorithm>());
+    if (failed) throw decoding_failure("Decoding failure");
+    std::vector<Return_type> r;
+    r.reserve(n);
+    for (uint8_t v : out) r.push_back(Return_type(v));
+    return r;
+  }
+
   // ---- one Eb/N0 point of awgn_simulation (simulation.c++:112-149), fused on the GPU
   ccgpu_counters awgn_point(double ebno_db, uint64_t frames, uint64_t seed = 0, uint32_t point = 0,
                             uint64_t frame0 = 0) const {
@@ -255,6 +275,21 @@ public:
   }
 
 private:
+  template <typename In>
+  void correct_erased(const In &b, const std::vector<unsigned> &er, uint8_t *out, uint8_t *failed, std::true_type) const {
+    std::vector<float> y(b.begin(), b.end());
+    for (unsigned e : er) y.at(e) = 0.0f;
+    correct_batch(y.data(), 1, out, failed);
+  }
+  template <typename In>
+  void correct_erased(const In &b, const std::vector<unsigned> &er, uint8_t *out, uint8_t *failed, std::false_type) const {
+    if (er.size() > 30) throw decoding_failure("Number of erasures exceed what the engine supports (30).");
+    std::vector<uint8_t> w, pos(30, 0);
+    for (const auto &e : b) w.push_back(std::is_signed<typename In::value_type>::value ? (e < 0 ? 1 : 0) : static_cast<uint8_t>(e));
+    for (size_t i = 0; i < er.size(); ++i) pos[i] = static_cast<uint8_t>(er[i]);
+    const uint8_t cnt = static_cast<uint8_t>(er.size());
+    h_->ctx->check(ccgpu_gf_decode_erasures(h_->ctx->get(), h_->code, w.data(), 1, pos.data(), &cnt, 30, out, nullptr, failed));
+  }
   template <typename In> void correct_one(const In &b, uint8_t *out, uint8_t *failed, std::true_type) const {
     std::vector<float> y(b.begin(), b.end());
     correct_batch(y.data(), 1, out, failed);

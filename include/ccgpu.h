@@ -137,6 +137,11 @@ int ccgpu_code_get_info(const ccgpu_code *code, ccgpu_code_info *out);
  * (simulation.c++:98) and parsed by the CLI (benchmark.c++:214-240). */
 int ccgpu_code_to_string(const ccgpu_code *code, const char *tag, char *buf, size_t cap);
 int ccgpu_code_H(const ccgpu_code *code, uint8_t *out /* h_rows x n */);
+/* cyclic::H_alt<T>() -- codes/cyclic.h:361-385, the parity-check matrix from the roots of g(x): t*q rows.
+ * as_reference = 1 reproduces the reference bit for bit (its from_power reduces exponents mod 2^q,
+ * math/galois.h:182-184, so rows are wrong for exponents >= 2^q); 0 reduces mod n (a valid matrix).
+ * out may be NULL to query *rows.  Feed the result to ccgpu_code_from_dense to decode on it. */
+int ccgpu_code_H_alt(const ccgpu_code *code, int as_reference, uint8_t *out, uint32_t *rows);
 /* which: 0 = g(x), 1 = h(x); coefficients low degree first; returns the count or <0 */
 int ccgpu_code_poly(const ccgpu_code *code, int which, uint16_t *out, size_t cap);
 /* exp[2*2^q], log[2^q] of math::ef_element<2,q> (math/galois.h:269-301); poly 0 = default table :18-20 */

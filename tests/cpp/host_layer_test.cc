@@ -92,6 +92,28 @@ static int gpu_tests(const std::string &dir) {
     w[3] = 7; w[100] = 200; w[254] = 1;
     CHECK(code.correct(w) == std::vector<uint8_t>(255, 0));
   }
+  // exercises.c++ task 6.7 / 6.8: RS(7,3) with erasures through correct(b, erasures)
+  {
+    rs<3, errors<2>, berlekamp_massey_tag> code;
+    // alpha^p table of GF(8), primitive polynomial x^3 + x + 1: 1 2 4 3 6 7 5
+    const uint8_t a[7] = { 1, 2, 4, 3, 6, 7, 5 };
+    const std::vector<uint8_t> word({ a[6], a[2], a[2], a[5], a[4], a[6], a[5] });
+    std::vector<uint8_t> b(word);
+    const std::vector<unsigned> erasures({ 5, 4, 3, 2 });
+    for (unsigned e : erasures) b[e] = 0;
+    CHECK(code.correct(b, erasures) == word);
+    const std::vector<uint8_t> b8({ a[2], a[0], a[4], a[0], a[5], a[0], a[2] });
+    const std::vector<uint8_t> want8({ a[2], a[5], a[4], a[6], a[5], a[6], a[2] });
+    CHECK(code.correct(b8, std::vector<unsigned>({ 1, 3 })) == want8);
+  }
+  // soft decoding with erasures: the erased positions get channel value 0 (cyclic.h:261-262)
+  {
+    primitive_bch<6, errors<5>, normalized_min_sum_tag<50, std::ratio<8, 10> > > code;
+    std::vector<float> y(63, 1.0f);
+    y[7] = -3.0f;
+    y[20] = -2.0f;
+    CHECK(code.correct(y, std::vector<unsigned>({ 7, 20 })) == std::vector<uint8_t>(63, 0));
+  }
   // soft decoders through the type-erased decoder, like simulation.c++:124-136
   {
     decoder d = primitive_bch<6, errors<5>, normalized_min_sum_tag<50, std::ratio<8, 10> > >();

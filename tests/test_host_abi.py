@@ -80,3 +80,19 @@ def test_sigma():
     import oracle
     for rate, eb in ((36 / 63, 4.0), (7 / 15, 1.0), (131 / 255, 8.0)):
         assert cc.sigma(rate, eb) == oracle.sigma(rate, eb)
+
+
+@pytest.mark.parametrize("name", ["bch_15_7", "bch_31_16", "bch_63_45", "bch_127_106", "bch_255_131"])
+def test_h_alt(name, catalogue, golden_codes):
+    """H_alt: as_reference reproduces the reference's matrix bit for bit (including its exponent bug, SURVEY
+    C4); the corrected construction is orthogonal to every codeword"""
+    e = catalogue[name]
+    c = cc.host_bch(e["q"], **({"errors": e["cap_value"]} if e["cap_kind"] == 0 else {"dmin": e["cap_value"]}))
+    assert np.array_equal(c.H_alt(as_reference=True), golden_H(golden_codes, catalogue, name, alt=True))
+    fixed = c.H_alt(as_reference=False)
+    msgs = np.eye(c.l, dtype=np.uint8)
+    words = c.encode(msgs)
+    assert not ((fixed.astype(np.int64) @ words.T.astype(np.int64)) % 2).any()
+    assert not ((c.H().astype(np.int64) @ words.T.astype(np.int64)) % 2).any()
+    if name == "bch_63_45":  # SURVEY fact 7: the reference's H_alt violates 254 of 810 checks for (63,45)
+        assert int(((c.H_alt(as_reference=True).astype(np.int64) @ words.T.astype(np.int64)) % 2).sum()) == 254
