@@ -85,5 +85,6 @@ def gpu_point_fn(code, variant="MS", alpha=1.0, beta=0.0, max_iter=50, stop_rule
         if frames > 0:
             code.awgn_point(ebno, frames, variant, alpha, beta, max_iter, stop_rule, seed=seed, point=point,
                             frame0=frame0, out=out)
+            code.ctx.sync()  # the launch is asynchronous on the context's stream, not on torch's
         return out
     return fn

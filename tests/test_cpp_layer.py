@@ -57,3 +57,29 @@ def test_cli_bitflip_and_awgn(bins, tmp_path, kat):
     assert lines[0] == "   ebno                   wer" and len(lines) >= 10
     wers = [float(x.split()[1]) for x in lines[1:]]
     assert wers[0] > 0.3 and wers[-1] < 1e-3
+
+
+@pytest.mark.gpu
+def test_python_sweep_equals_cli_sweep(bins, tmp_path):
+    """the same sweep driven from C++ (cc::awgn_simulation via the CLI, three pool threads sharing one
+    context) and from Python (channelcoding_b200.simulation, the multi-GPU driver with world size 1) must
+    write byte-identical "<name>.log" files: same schedule, same Philox frames, same counters"""
+    import channelcoding_b200 as cc
+    from channelcoding_b200 import simulation
+    cli_dir = tmp_path / "cli"
+    py_dir = tmp_path / "py"
+    cli_dir.mkdir()
+    py_dir.mkdir()
+    r = subprocess.run([bins["benchmark"], "--k", "5", "--dmin", "7", "--algorithm", "ms", "--algorithm", "nms",
+                        "--algorithm", "scms2", "--max-samples", "200000", "--seed", "11", "--threads", "3", "--out",
+                        str(cli_dir)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ctx = cc.Context(0)
+    code = ctx.bch(5, dmin=7)
+    for tag, variant, alpha in (("MS", "MS", 1.0), ("NMS", "NMS", 0.8), ("SCMS2", "SCMS2", 1.0)):
+        name = code.to_string(tag)
+        res = simulation.awgn_sweep(simulation.gpu_point_fn(code, variant, alpha, seed=11), name, code.rate, cap=200000,
+                                    log_dir=str(py_dir))
+        assert open(py_dir / (name + ".log")).read() == open(cli_dir / (name + ".log")).read(), tag
+        assert res[0]["ebno"] == 1.0 and res[0]["frames"] == 10000 and res[-1]["wer"] < res[0]["wer"]
+    ctx.close()
