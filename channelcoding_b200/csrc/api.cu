@@ -641,6 +641,9 @@ int ccgpu_awgn_point(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_para
   fill_decoder(mp, code, params);
   mp.src = SRC_PHILOX;
   mp.sigma = static_cast<float>(ccgpu_sigma(code->spec.rate, ebno_db));  // simulation.c++:113-115
+  // the min-sum family is scale invariant and takes the raw channel values like the reference; the
+  // sum-product extension needs log-likelihood ratios 2 y / sigma^2
+  mp.llr_scale = params->variant == CCGPU_SPA ? 2.0f / (mp.sigma * mp.sigma) : 1.0f;
   mp.seed = seed;
   mp.point = point;
   mp.frame0 = frame0;

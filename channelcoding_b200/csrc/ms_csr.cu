@@ -77,7 +77,7 @@ __global__ void ms_csr_kernel(const __grid_constant__ MsParams p, const CsrView 
     } else if (p.src == SRC_PHILOX) {
       for (int b = tid; b < ((n + 3) >> 2); b += nt) {
         const float4 v = awgn_block(p.seed, p.point, p.frame0 + fr, b, p.sigma);
-        const float vv[4] = { v.x, v.y, v.z, v.w };
+        const float vv[4] = { v.x * p.llr_scale, v.y * p.llr_scale, v.z * p.llr_scale, v.w * p.llr_scale };
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           if (4 * b + e < n) ybuf[4 * b + e] = vv[e];

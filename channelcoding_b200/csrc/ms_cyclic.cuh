@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
           if (bv && ((initm >> src_lane) & 1u)) {
             const float4 v = awgn_block(p.seed, p.point, p.frame0 + static_cast<uint64_t>(fr), blk, p.sigma);
             const int c0 = f * N + 4 * blk;
-            const float vv[4] = { v.x, v.y, v.z, v.w };
+            const float vv[4] = { v.x * p.llr_scale, v.y * p.llr_scale, v.z * p.llr_scale, v.w * p.llr_scale };
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               if (4 * blk + e < N) {

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(S::THREADS) ms_cyclic_cta_kernel(const __grid_
     } else if (p.src == SRC_PHILOX) {
       for (int b = tid; b < NBLK; b += THREADS) {
         const float4 v = awgn_block(p.seed, p.point, p.frame0 + static_cast<uint64_t>(frame), b, p.sigma);
-        const float vv[4] = { v.x, v.y, v.z, v.w };
+        const float vv[4] = { v.x * p.llr_scale, v.y * p.llr_scale, v.z * p.llr_scale, v.w * p.llr_scale };
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           if (4 * b + e < N) ybuf[4 * b + e] = vv[e];

@@ -24,11 +24,11 @@ struct MsParams {
   // ---- frame source
   const float *y;      // SRC_HBM: frames x n
   float sigma;         // SRC_PHILOX
+  float llr_scale;     // SRC_PHILOX: y is multiplied by this (2 / sigma^2 for sum-product, else 1)
   uint32_t point;
   uint64_t seed, frame0;
   uint64_t frames;     // frames of this launch
   uint32_t flip_weight;  // SRC_BITFLIP: patterns of this weight, frame index = lexicographic rank
-  uint32_t pad0;
   // ---- outputs (nullable)
   uint8_t *bits;       // frames x n
   float *L;            // frames x n

@@ -182,7 +182,9 @@ int ccgpu_awgn_llr(ccgpu_ctx *ctx, uint32_t n, double sigma, uint64_t seed, uint
 
 /* one Eb/N0 point of awgn_simulation::operator() (simulation.c++:112-149) for global frames
  * [frame0, frame0 + frames): channel + decode + error test fused on chip; only counters leave
- * the GPU.  `out` may be a host or device pointer (device: accumulated into, caller zeroes). */
+ * the GPU.  `out` may be a host or device pointer (device: accumulated into, caller zeroes).
+ * The min-sum variants get the raw channel values y like the reference's decoders; for CCGPU_SPA the
+ * values are scaled to log-likelihood ratios 2 y / sigma^2 first. */
 int ccgpu_awgn_point(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, double ebno_db,
                      uint64_t seed, uint32_t point, uint64_t frame0, uint64_t frames, ccgpu_counters *out);
 
