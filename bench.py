@@ -319,6 +319,12 @@ def main():
             "alu": {"model": "avg_iters*(11E+2n) lane-ops/frame (SURVEY 8d)", "lane_ops_per_frame": lane_ops,
                     "achieved_lane_ops_per_s": value / world * lane_ops, "peak_lane_ops_per_s": alu_peak,
                     "frac": value / world * lane_ops / alu_peak},
+            # the pipe that actually binds (ncu: LSU 82.5 %, issue 83 %): 79 shared-memory wavefronts per
+            # frame-iteration (36 VN/CN loads, 36 column-sum read-modify-writes, 7 column phase) against one
+            # wavefront per SM per cycle
+            "smem": {"wavefronts_per_frame_iteration": 79, "achieved_wavefronts_per_s": value / world * iters_exec * 79,
+                     "peak_wavefronts_per_s": 148 * sm_max * 1e6,
+                     "frac": value / world * iters_exec * 79 / (148 * sm_max * 1e6)},
             "clocks": clocks,
         }
         if not args.no_cpu:
