@@ -1,9 +1,9 @@
 // ms_csr.cu -- K2g: min-sum / sum-product decoder for an ARBITRARY dense 0/1 parity-check matrix.
 //
 // Same contract as ms_cyclic.cuh (reference codes/soft_decision.h:161-202) but no structural
-// assumption on H: used for H_alt() (codes/cyclic.h:361-385), redundant / multiple-bases
-// matrices handed in through ccgpu_code_from_dense, the 124 x 255 matrix of BCH(255,131), and
-// as the home of the sum-product (tanh rule) extension.
+// assumption on H: used for H_alt() (codes/cyclic.h:361-385) and any other matrix handed in through
+// ccgpu_code_from_dense whose shape has no compiled cyclic kernel (row-permuted, multiple-bases, ...),
+// for every variant including the sum-product (tanh rule) extension.
 //
 // Mapping: one CTA per frame, persistent (grid-strided frames).  All messages of the frame stay
 // in shared memory:  q/r per edge in ELL layout [slot j][row r] (conflict free for thread = row),

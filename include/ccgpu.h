@@ -14,8 +14,9 @@
  *     reference's `decoding_failure` exception (codes/codes.h:28-36) is a normal outcome that the
  *     simulation counts (simulation/simulation.c++:133-135).
  *   - the caller owns every buffer.  Data pointers may be host or device pointers (detected with
- *     cudaPointerGetAttributes); host buffers are staged through pinned memory and the call
- *     returns after the results are in the caller's buffer; with device buffers the work is
+ *     cudaPointerGetAttributes); host buffers are cut into chunks that rotate over three staging slots
+ *     (copy in / decode / copy out overlap; pin the host memory to get asynchronous copies) and the
+ *     call returns after the results are in the caller's buffer; with device buffers the work is
  *     enqueued on the context's stream and the call returns immediately (ccgpu_sync to wait).
  *   - a context is bound to one CUDA device and one stream and is internally locked, so the
  *     reference's pool threads (simulation/simulation.c++:240-273) may share it.
@@ -96,7 +97,8 @@ typedef struct {
   uint32_t edges;      /* ones in H */
   uint32_t h_kind;     /* 0 = cyclic taps without wrap (cyclic.h:346-359), 1 = cyclic with wrap
                           (redundant rows), 2 = general (CSR) */
-  uint32_t kernel;     /* 0 = none (algebraic only), 1 = ms_cyclic (lane per row), 2 = ms_csr */
+  uint32_t kernel;     /* 0 = host-only code, 1 = shape-specialised cyclic kernel (ms_cyclic / ms_cyclic_cta),
+                          2 = general kernel (ms_csr) */
   double rate;         /* l / n (cyclic.h:274) */
 } ccgpu_code_info;
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """tools/sweep.py -- Eb/N0 waterfall sweep sharded over GPUs (BASELINE.json config 5).
 
-    python tools/sweep.py --q 8 --t 18 --variant NMS --alpha 0.8 --start 0 --stop 8 --step 0.5
+    python tools/sweep.py --q 8 --t 18 --variant NMS --alpha 0.8 --ebno-from 0 --ebno-to 8 --ebno-step 0.5
     torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/sweep.py ...
 
 Every Eb/N0 point is simulated in rounds of --batch frames (split evenly over the ranks by global frame
@@ -27,9 +27,9 @@ def main():
     ap.add_argument("--beta", type=float, default=0.0)
     ap.add_argument("--max-iter", type=int, default=50)
     ap.add_argument("--stop-rule", type=int, default=0)
-    ap.add_argument("--start", type=float, default=0.0)
-    ap.add_argument("--stop", type=float, default=8.0)
-    ap.add_argument("--step", type=float, default=0.5)
+    ap.add_argument("--ebno-from", type=float, default=0.0)  # (torchrun's own parser claims --start*)
+    ap.add_argument("--ebno-to", type=float, default=8.0)
+    ap.add_argument("--ebno-step", type=float, default=0.5)
     ap.add_argument("--batch", type=int, default=1 << 24)
     ap.add_argument("--min-errors", type=int, default=100)
     ap.add_argument("--max-frames", type=float, default=1e9)
@@ -52,8 +52,8 @@ def main():
     ctx.use_torch_stream()
     code = ctx.bch(a.q, errors=a.t)
     dev = torch.device("cuda", local)
-    point, eb = 0, a.start
-    while eb < a.stop + a.step / 2:
+    point, eb = 0, a.ebno_from
+    while eb < a.ebno_to + a.ebno_step / 2:
         total = torch.zeros(8, dtype=torch.int64, device=dev)
         done = 0
         t0 = time.perf_counter()
@@ -76,7 +76,7 @@ def main():
                               "avg_iterations": c[3] / c[0], "failures": c[4], "undetected": c[5], "n_gpus": world,
                               "seconds": el, "frames_per_s": c[0] / el}), flush=True)
         point += 1
-        eb += a.step
+        eb += a.ebno_step
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
