@@ -153,6 +153,53 @@ bool columns_covered(const CodeSpec &s) {
   return true;
 }
 
+// channel + hard decision (codes/codes.h:43-52: bit = y < 0): one thread = one Philox block = four symbols
+__global__ void __launch_bounds__(kAwgnThreads) awgn_hard_kernel(uint8_t *__restrict__ words, uint32_t n, float sigma,
+                                                                uint64_t seed, uint32_t point, uint64_t frame0,
+                                                                uint64_t frames) {
+  const uint32_t nblk = (n + 3) >> 2;
+  const uint64_t total = frames * nblk;
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t f = i / nblk;
+    const uint32_t blk = static_cast<uint32_t>(i - f * nblk);
+    const float4 v = awgn_block(seed, point, frame0 + f, blk, sigma);
+    const float vv[4] = { v.x, v.y, v.z, v.w };
+    uint8_t *dst = words + f * n + 4 * blk;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (4 * blk + e < n) dst[e] = vv[e] < 0.0f ? 1 : 0;
+  }
+}
+
+// word-error test of simulation.c++:126-135 over decoded words (all-zero codeword sent): one warp per word
+__global__ void __launch_bounds__(256) count_words_kernel(const uint8_t *__restrict__ words, const uint8_t *__restrict__ failed,
+                                                          uint32_t n, uint64_t count, unsigned long long *counters) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t warps = static_cast<uint64_t>(gridDim.x) * (blockDim.x >> 5);
+  unsigned long long c_frames = 0, c_ferr = 0, c_berr = 0, c_fail = 0, c_und = 0;
+  for (uint64_t w = blockIdx.x * static_cast<uint64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); w < count; w += warps) {
+    unsigned nz = 0;
+    for (uint32_t i = lane; i < n; i += 32) nz += words[w * n + i] != 0;
+    for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+    if (lane == 0) {
+      const bool f = failed[w] != 0;
+      c_frames += 1;
+      c_fail += f;
+      c_berr += nz;
+      c_ferr += (f || nz) ? 1 : 0;
+      c_und += (!f && nz) ? 1 : 0;
+    }
+  }
+  if (lane == 0) {
+    if (c_frames) atomicAdd(counters + C_FRAMES, c_frames);
+    if (c_ferr) atomicAdd(counters + C_FRAME_ERR, c_ferr);
+    if (c_berr) atomicAdd(counters + C_BIT_ERR, c_berr);
+    if (c_fail) atomicAdd(counters + C_FAIL, c_fail);
+    if (c_und) atomicAdd(counters + C_UNDETECTED, c_und);
+  }
+}
+
 // pick the cyclic kernel instantiations (one per vertical-node flavour) compiled for exactly this
 // H: same n, same tap offsets, and either the same number of rows without wrap-around or a
 // redundant (run-time rows, wrap-around) shape.  Nothing fits -> CSR kernel.
@@ -739,6 +786,47 @@ int ccgpu_gf_decode_erasures(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8
 int ccgpu_gf_decode(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8_t *words, uint64_t count,
                     uint8_t *corrected, uint8_t *n_errors, uint8_t *failed) {
   return ccgpu_gf_decode_erasures(ctx, code, words, count, nullptr, nullptr, 0, corrected, n_errors, failed);
+}
+
+int ccgpu_awgn_point_hard(ccgpu_ctx *ctx, const ccgpu_code *code, double ebno_db, uint64_t seed, uint32_t point,
+                          uint64_t frame0, uint64_t frames, ccgpu_counters *out) {
+  if (!ctx || !code || !out) return fail(ctx, CCGPU_ERR_INVALID, "null argument");
+  if (code->ctx != ctx) return fail(ctx, CCGPU_ERR_INVALID, "code was not created on this context");
+  if (code->spec.family != 0) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "hard-decision AWGN points need a binary BCH code");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  const size_t n = code->spec.n;
+  const bool dev = is_device_ptr(out);
+  unsigned long long *counters = dev ? reinterpret_cast<unsigned long long *>(out) : ctx->d_counters;
+  if (!dev) CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(ccgpu_counters), ctx->stream));
+  const uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>(frames, 1), uint64_t(1) << 22);
+  int rc = ensure_stage(ctx, chunk * (2 * n + 2) + 64);
+  if (rc) return rc;
+  uint8_t *d_words = static_cast<uint8_t *>(ctx->d_stage);
+  uint8_t *d_out = d_words + chunk * n;
+  uint8_t *d_ne = d_out + chunk * n;
+  uint8_t *d_fail = d_ne + chunk;
+  const float sigma = static_cast<float>(ccgpu_sigma(code->spec.rate, ebno_db));
+  for (uint64_t f0 = 0; f0 < frames; f0 += chunk) {
+    const uint64_t nf = std::min(chunk, frames - f0);
+    const uint64_t blocks = (nf * ((n + 3) / 4) + kAwgnThreads - 1) / kAwgnThreads;
+    awgn_hard_kernel<<<static_cast<unsigned>(std::min<uint64_t>(blocks, uint64_t(ctx->sm_count) * 16)), kAwgnThreads, 0,
+                       ctx->stream>>>(d_words, static_cast<uint32_t>(n), sigma, seed, point, frame0 + f0, nf);
+    CU(cudaGetLastError());
+    rc = gf_launch(code->gf, d_words, nf, nullptr, nullptr, 0, d_out, d_ne, d_fail, ctx->sm_count, ctx->stream);
+    if (rc == -3) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "code not supported by the algebraic kernel");
+    if (rc != 0) return cuda_fail(ctx, cudaGetLastError(), "gf_launch");
+    count_words_kernel<<<static_cast<unsigned>(std::min<uint64_t>((nf + 7) / 8, uint64_t(ctx->sm_count) * 8)), 256, 0, ctx->stream>>>(
+        d_out, d_fail, static_cast<uint32_t>(n), nf, counters);
+    CU(cudaGetLastError());
+    ctx->launches += 3;
+  }
+  if (!dev) {
+    CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(ccgpu_counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out = *ctx->h_counters;
+  }
+  return CCGPU_OK;
 }
 
 int ccgpu_code_set_recheck(ccgpu_code *code, int enable) {

@@ -234,6 +234,13 @@ class Code:
                                                     frame0, frames, C.addressof(c)))
         return c.as_dict()
 
+    def awgn_point_hard(self, ebno_db, frames, seed=0, point=0, frame0=0):
+        """one Eb/N0 point with hard decisions + algebraic decoding (the BM/PGZ/Euklid decoders in the sweep)"""
+        c = Counters()
+        self.ctx._check(_lib.lib().ccgpu_awgn_point_hard(self.ctx._h, self._h, float(ebno_db), seed, point, frame0, frames,
+                                                         C.addressof(c)))
+        return c.as_dict()
+
     def bitflip_point(self, weight, variant="MS", alpha=1.0, beta=0.0, max_iter=50,
                       stop_rule=STOP_REF_ZERO_OVERLAP, first=0, count=0):
         """one error weight of bitflip_simulation (simulation.c++:156-213) -> counters"""

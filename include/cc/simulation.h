@@ -56,34 +56,12 @@ class decoder {
   template <typename T> class decoder_model : public decoder_concept {
     T implementation;
 
-    // hard-decision tags: channel on the GPU (K1), hard decision on the host (codes.h:43-52), batched
-    // algebraic decode on the GPU (K4), error test on the host (simulation.c++:126-135)
+    // hard-decision tags: channel, hard decision (codes.h:43-52), algebraic decode and the error test of
+    // simulation.c++:126-135 all on the device (ccgpu_awgn_point_hard)
     ccgpu_counters hard_point(double ebno_db, uint64_t frames, uint64_t seed, uint32_t point, uint64_t frame0) const {
-      const unsigned n_ = T::n;
       ccgpu_counters c{};
-      const uint64_t chunk = 1u << 18;
-      std::vector<float> y;
-      std::vector<uint8_t> w, out, failed;
-      for (uint64_t f0 = 0; f0 < frames; f0 += chunk) {
-        const uint64_t nf = std::min(chunk, frames - f0);
-        y.resize(nf * n_);
-        w.resize(nf * n_);
-        out.resize(nf * n_);
-        failed.resize(nf);
-        implementation.ctx()->check(ccgpu_awgn_llr(implementation.ctx()->get(), n_, ccgpu_sigma(implementation.rate, ebno_db),
-                                                   seed, point, frame0 + f0, nf, y.data()));
-        for (size_t i = 0; i < y.size(); ++i) w[i] = y[i] < 0 ? 1 : 0;
-        implementation.correct_batch(w.data(), nf, out.data(), failed.data());
-        for (uint64_t f = 0; f < nf; ++f) {
-          unsigned bits = 0;
-          for (unsigned i = 0; i < n_; ++i) bits += out[f * n_ + i] != 0;
-          c.frames++;
-          c.failures += failed[f];
-          c.bit_errors += bits;
-          c.frame_errors += (failed[f] || bits) ? 1 : 0;
-          c.undetected += (!failed[f] && bits) ? 1 : 0;
-        }
-      }
+      implementation.ctx()->check(ccgpu_awgn_point_hard(implementation.ctx()->get(), implementation.handle(), ebno_db, seed,
+                                                        point, frame0, frames, &c));
       return c;
     }
     template <typename U = T>

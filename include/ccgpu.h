@@ -190,6 +190,12 @@ int ccgpu_awgn_llr(ccgpu_ctx *ctx, uint32_t n, double sigma, uint64_t seed, uint
 int ccgpu_awgn_point(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, double ebno_db,
                      uint64_t seed, uint32_t point, uint64_t frame0, uint64_t frames, ccgpu_counters *out);
 
+/* the same Eb/N0 point for the HARD-decision tags (BM / PGZ / Euklid decoders of benchmark.c++:29-64 inside
+ * awgn_simulation): channel, hard decision (codes/codes.h:43-52: bit = y < 0), algebraic decode
+ * (cyclic.h:207-252) and the error test, all on the device; binary BCH codes.  iterations stays 0. */
+int ccgpu_awgn_point_hard(ccgpu_ctx *ctx, const ccgpu_code *code, double ebno_db, uint64_t seed, uint32_t point,
+                          uint64_t frame0, uint64_t frames, ccgpu_counters *out);
+
 /* one weight class of bitflip_simulation::operator() (simulation.c++:156-213): all C(n, weight)
  * inputs x = -2*bit + 1, decoded and counted; patterns [first, first + count) in the
  * lexicographic order of std::next_permutation (count 0 = all). */

@@ -422,3 +422,24 @@ def test_uncovered_columns_use_the_general_stop_test(ctx, catalogue, golden_code
         assert_same(code.decode(y, "NMS", 0.8, 0.0, 20, stop), oracle.min_sum(H, y, "NMS", 0.8, 0.0, 20, stop), "partial H")
     gb, gL, gi, gf = code.decode(y, "NMS", 0.8, 0.0, 20, 0)
     assert (gf == 0).any() and gb[gf == 0][:, 50:].all()
+
+
+def test_hard_decision_awgn_point(ctx, catalogue):
+    """ccgpu_awgn_point_hard (channel + hard decision + algebraic decode + count on the device) ==
+    K1 -> host hard decision (codes.h:43-52) -> ccgpu_gf_decode -> host count (simulation.c++:126-135)"""
+    import channelcoding_b200 as cc
+    for name, eb, frames in (("bch_31_16", 3.0, 50000), ("bch_63_36", 4.0, 40000), ("bch_127_64", 5.0, 20000),
+                             ("bch_255_131", 6.0, 5000)):
+        e = catalogue[name]
+        code = make_code(ctx, e)
+        y = ctx.awgn_llr(e["n"], np.float32(cc.sigma(e["rate"], eb)), seed=9, point=4, frame0=77, frames=frames)
+        out, nerr, failed = code.gf_decode((y < 0).astype(np.uint8))
+        nz = (out != 0).sum(axis=1)
+        c = code.awgn_point_hard(eb, frames, seed=9, point=4, frame0=77)
+        assert c["frames"] == frames and c["iterations"] == 0
+        assert c["failures"] == int(failed.sum())
+        assert c["bit_errors"] == int(nz.sum())
+        assert c["frame_errors"] == int(((failed == 1) | (nz > 0)).sum())
+        assert c["undetected"] == int(((failed == 0) & (nz > 0)).sum())
+        halves = [code.awgn_point_hard(eb, frames // 2, seed=9, point=4, frame0=77 + i * (frames // 2)) for i in range(2)]
+        assert all(halves[0][k] + halves[1][k] == c[k] for k in c)
