@@ -72,8 +72,13 @@ __device__ __forceinline__ unsigned long long binom(unsigned n, unsigned r) {
   return v;
 }
 
+// resident CTAs per SM the register allocation aims at: 8 (64 registers) while the row's messages fit
+template <class S, int VN> constexpr int ms_min_blocks() {
+  return (S::RPL * S::W * ((VN == VN_SC || VN == VN_SPA) ? 2 : 1) + (CCGPU_MS_YREG && VN != VN_SC && !S::WRAP ? S::RPL * S::W : 0) <= 36) ? 8 : 1;
+}
+
 template <class S, int VN>
-__global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_constant__ MsParams p) {
+__global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_kernel(const __grid_constant__ MsParams p) {
   constexpr int N = S::N, W = S::W, RPL = S::RPL, NP = S::NP, FPW = S::FPW;
   constexpr bool WRAP = S::WRAP, SC = VN == VN_SC, SPA = VN == VN_SPA;
   // y of the row's W edges is loop invariant: keep it in registers when the budget allows (saves one
@@ -164,7 +169,8 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
   float r[RPL][W];
   float qold[(SC || SPA) ? RPL : 1][(SC || SPA) ? W : 1];  // previous q (SCMS) / prefix products (SPA)
   float yreg[YREG ? RPL : 1][YREG ? W : 1];
-  unsigned long long cnt_frames = 0, cnt_ferr = 0, cnt_berr = 0, cnt_iter = 0, cnt_fail = 0, cnt_und = 0;
+  // 32-bit per-warp counters (a warp sees far fewer than 2^32 / 50 frames per launch); widened at the end
+  unsigned cnt_frames = 0, cnt_ferr = 0, cnt_berr = 0, cnt_iter = 0, cnt_fail = 0, cnt_und = 0;
   constexpr int NBLK = (N + 3) >> 2;
 
   while (true) {
@@ -416,7 +422,7 @@ __global__ void __launch_bounds__(kMsThreads) ms_cyclic_kernel(const __grid_cons
 
   // ---------------- counters: warp reduce, one atomic per slot per warp
   if (p.counters != nullptr) {
-    unsigned long long v[6] = { cnt_frames, cnt_ferr, cnt_berr, cnt_iter, cnt_fail, cnt_und };
+    unsigned long long v[6] = { cnt_frames, cnt_ferr, cnt_berr, cnt_iter, cnt_fail, cnt_und };  // widen
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
       unsigned long long x = v[s];
