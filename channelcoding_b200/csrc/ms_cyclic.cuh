@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
           }
           if (rvalid[i] && wrapped == (pass == 1)) yrow[i][SOFF + off] = __fadd_rn(yrow[i][SOFF + off], r[i][j]);
         }
-        __syncwarp();
+        __syncwarp();  // required: without it the next step's loads overtake this step's stores (measured)
       }
     }
 
