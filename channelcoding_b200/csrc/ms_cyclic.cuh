@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
     // ============ (re)fill frame groups that finished
     const unsigned initm = __ballot_sync(kFull, active && need_init);
     if (initm) {
+      __syncwarp();  // the finished frame's y / S were read by other lanes (outputs): order those reads first
       if (p.src == SRC_HBM) {
 #pragma unroll
         for (int ps = 0; ps < NP; ++ps) {
