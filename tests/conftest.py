@@ -13,6 +13,13 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no built artefacts (they are git-ignored): build the product library (nvcc cross
+    # compiles without a GPU) and the test oracle once
+    from channelcoding_b200 import build as _build
+    if not os.path.exists(_build.LIB):
+        _build.build()
+    import oracle
+    oracle.build()
 
 
 @pytest.fixture(scope="session")
