@@ -443,3 +443,52 @@ def test_hard_decision_awgn_point(ctx, catalogue):
         assert c["undetected"] == int(((failed == 0) & (nz > 0)).sum())
         halves = [code.awgn_point_hard(eb, frames // 2, seed=9, point=4, frame0=77 + i * (frames // 2)) for i in range(2)]
         assert all(halves[0][k] + halves[1][k] == c[k] for k in c)
+
+
+def test_edge_cases_and_errors(ctx, catalogue):
+    """empty and single-frame batches, iteration limits, and the error contract of the ABI (an error code
+    plus ccgpu_last_error text, never an exception across the boundary, never a silent fallback)"""
+    import torch
+    import channelcoding_b200 as cc
+    code = make_code(ctx, catalogue["bch_63_36"])
+    H = code.H()
+    empty = code.decode(np.zeros((0, 63), np.float32), "NMS", 0.8)
+    assert empty[0].shape == (0, 63) and empty[3].shape == (0,)
+    assert code.awgn_point(4.0, 0, "NMS", 0.8)["frames"] == 0
+    rng = np.random.default_rng(8)
+    one = (1 + 0.8 * rng.standard_normal((1, 63))).astype(np.float32)
+    assert_same(code.decode(one, "NMS", 0.8), oracle.min_sum(H, one, "NMS", 0.8), "single frame")
+    y = (1 + 0.9 * rng.standard_normal((999, 63))).astype(np.float32)  # odd count: partial last warp / CTA
+    for mi in (1, 2, 255):
+        assert_same(code.decode(y, "OMS", 1.0, 0.02, mi), oracle.min_sum(H, y, "OMS", 1.0, 0.02, mi), "max_iter %d" % mi)
+    # HEAD behaviour of the reference (matrix.h:50 bug): exactly one iteration, never a failure
+    gb, gL, gi, gf = code.decode(y, "NMS", 0.8, 0.0, 1, cc.STOP_NONE)
+    assert not gf.any() and not gi.any()
+    for kwargs, text in (({"max_iter": 0}, "max_iter"), ({"max_iter": 256}, "max_iter"),
+                         ({"variant": "OMS", "beta": -0.1}, "beta"), ({"stop_rule": 7}, "stop rule")):
+        args = dict(variant="NMS", alpha=0.8, beta=0.0, max_iter=50, stop_rule=0)
+        args.update(kwargs)
+        with pytest.raises(cc.CcgpuError) as ei:
+            code.decode(y, **args)
+        assert ei.value.code == -1 and text in str(ei.value)
+    with pytest.raises(cc.CcgpuError) as ei:  # device input with a host output buffer
+        code.decode(torch.from_numpy(y).cuda(), "NMS", 0.8,
+                    out=(np.empty((999, 63), np.uint8), None, np.empty(999, np.uint8), np.empty(999, np.uint8)))
+    assert "device pointer" in str(ei.value)
+    other = cc.Context(0)
+    foreign = other.bch(6, errors=5)
+    foreign.ctx = ctx  # hand the other context's code to this context: the ABI must refuse it
+    with pytest.raises(cc.CcgpuError) as ei:
+        foreign.decode(y, "NMS", 0.8)
+    assert "not created on this context" in str(ei.value)
+    foreign.ctx = other
+    foreign.close()
+    other.close()
+    with pytest.raises(cc.CcgpuError):
+        ctx.rs(8, 200)  # 2t >= n
+    with pytest.raises(cc.CcgpuError):
+        ctx.bch(9, errors=2)  # q > 8
+    dense = ctx.from_dense(H, 36 / 63)
+    with pytest.raises(cc.CcgpuError) as ei:
+        dense.gf_decode(np.zeros((1, 63), np.uint8))
+    assert ei.value.code == -3  # CCGPU_ERR_UNSUPPORTED: no field / roots behind a dense matrix
