@@ -135,7 +135,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    per_thread = 300  # frames per thread per step: a bounded sample of the workload
+    per_thread = 1000  # frames per thread per step: a bounded sample of the workload (0.6 s per step here)
     for _ in range(args.warmup):
         cpu_reference(args.ebno, 1e9, per_thread)
     t0 = time.time()
