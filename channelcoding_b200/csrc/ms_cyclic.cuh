@@ -41,9 +41,36 @@
 #define CCGPU_MS_YREG 0  /* measured: +18 registers cost more occupancy than the saved LDS gains (profiles/r1_notes.md) */
 #endif
 
+#ifndef CCGPU_MS_PACK2
+#define CCGPU_MS_PACK2 1  /* VN adds as packed add.rn.f32x2 (FADD2): two edges per issue slot, same IEEE results */
+#endif
+#ifndef CCGPU_MS_CN_PAIR
+#define CCGPU_MS_CN_PAIR 1
+#endif
+#ifndef CCGPU_MS_VOLATILE_COLSUM
+#define CCGPU_MS_VOLATILE_COLSUM 1  /* see VOLCS in the kernel */
+#endif
+
 namespace ccgpu {
 
 constexpr unsigned kFull = 0xffffffffu;
+
+// packed single-precision add/sub of sm_100 (add.rn.f32x2 -> FADD2): each half is the same IEEE
+// round-to-nearest operation as __fadd_rn / __fsub_rn, so the results stay bit-identical
+__device__ __forceinline__ void sub2_rn(float a0, float a1, float b0, float b1, float &d0, float &d1) {
+  unsigned long long A, B, D;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(D) : "l"(A), "l"(B));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
+}
+__device__ __forceinline__ void add2_rn(float a0, float a1, float b0, float b1, float &d0, float &d1) {
+  unsigned long long A, B, D;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(A) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(B) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(D) : "l"(A), "l"(B));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(D));
+}
 
 __device__ __forceinline__ float xor_sign(float v, unsigned signbits) {
   return __uint_as_float(__float_as_uint(v) ^ (signbits & 0x80000000u));
@@ -63,6 +90,18 @@ __device__ __forceinline__ float cn_magnitude(const MsParams &p, float m) {
     return static_cast<float>(d > 0.0 ? d : 0.0);
   }
   return m;
+}
+// the offset rule in double (:245-251), kept out of line so that the other variants do not issue its
+// predicated-off FP64 sequence twice per row and iteration
+static __device__ __noinline__ float2 cn_offset_pair(double beta, float m1, float m2) {
+  const double d1 = static_cast<double>(m1) - beta, d2 = static_cast<double>(m2) - beta;
+  return make_float2(static_cast<float>(d1 > 0.0 ? d1 : 0.0), static_cast<float>(d2 > 0.0 ? d2 : 0.0));
+}
+// fn_h applied to min1 and min2 of a row at once
+__device__ __forceinline__ float2 cn_magnitude_pair(const MsParams &p, float m1, float m2) {
+  if (p.variant == V_NMS || p.variant == V_NMS2D) return make_float2(__fmul_rn(p.alpha_f, m1), __fmul_rn(p.alpha_f, m2));
+  if (p.variant == V_OMS) return cn_offset_pair(p.beta_d, m1, m2);
+  return make_float2(m1, m2);
 }
 
 __device__ __forceinline__ unsigned long long binom(unsigned n, unsigned r) {
@@ -84,6 +123,11 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
   // y of the row's W edges is loop invariant: keep it in registers when the budget allows (saves one
   // shared-memory load per edge and iteration)
   constexpr bool YREG = CCGPU_MS_YREG && !SC && !WRAP && RPL * W <= 32;
+  // ordered column sums: with one row per lane the read-modify-write chain goes through VOLATILE accesses, which
+  // ptxas keeps in program order, instead of one __syncwarp per tap (ptxas proves the warp converged and turns
+  // each of those into a NOP issue slot; measured +5 % on BCH(63,36)).  Two or more rows per lane keep the
+  // __syncwarp form: volatile would serialise the rows of one step as well (measured -26 % on BCH(127,64)).
+  constexpr bool VOLCS = CCGPU_MS_VOLATILE_COLSUM && RPL == 1;
   constexpr int ITEMS = FPW * N;            // columns handled by this warp, <= 32 * NP
   constexpr int SOFF = 32 * NP;             // S lives SOFF floats after y
   using T = typename S::taps;
@@ -280,15 +324,33 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
     for (int i = 0; i < RPL; ++i) {
       float m1 = FLT_MAX, m2 = FLT_MAX;
       unsigned par = 0;
+      float qv[W];
+      // ---- q_j = (S[c_j] - r_j) + y[c_j]  (:135-136), two edges per packed instruction
+      constexpr int WP = CCGPU_MS_PACK2 ? (W & ~1) : 0;
 #pragma unroll
-      for (int j = 0; j < W; ++j) {
+      for (int j = 0; j < WP; j += 2) {
+        int off0 = T::get(j), off1 = T::get(j + 1);
+        if (WRAP && row[i] + off0 >= N) off0 -= N;
+        if (WRAP && row[i] + off1 >= N) off1 -= N;
+        float e0, e1;
+        sub2_rn(yrow[i][SOFF + off0], yrow[i][SOFF + off1], r[i][j], r[i][j + 1], e0, e1);
+        if (VN == VN_2D) {  // normalised_vertical (:215-218); scalar on purpose: ptxas contracts a packed
+          e0 = __fmul_rn(p.beta_f, e0);  // mul.rn.f32x2 + add.rn.f32x2 pair into FFMA2 (one rounding), which
+          e1 = __fmul_rn(p.beta_f, e1);  // the reference does not do
+        }
+        add2_rn(e0, e1, YREG ? yreg[i][j] : yrow[i][off0], YREG ? yreg[i][j + 1] : yrow[i][off1], qv[j], qv[j + 1]);
+      }
+#pragma unroll
+      for (int j = WP; j < W; ++j) {
         int off = T::get(j);
         if (WRAP && row[i] + off >= N) off -= N;
-        const float s = yrow[i][SOFF + off];
-        const float yy = YREG ? yreg[i][j] : yrow[i][off];
-        float e = __fsub_rn(s, r[i][j]);                      // exclusive column sum (:135)
-        if (VN == VN_2D) e = __fmul_rn(p.beta_f, e);          // normalised_vertical (:215-218)
-        float q = __fadd_rn(e, yy);                           // unmodified_vertical (:205-209)
+        float e = __fsub_rn(yrow[i][SOFF + off], r[i][j]);
+        if (VN == VN_2D) e = __fmul_rn(p.beta_f, e);
+        qv[j] = __fadd_rn(e, YREG ? yreg[i][j] : yrow[i][off]);
+      }
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        float q = qv[j];
         if (SC) {
           const float qo = qold[i][j];
           if (p.variant == V_SCMS1) {                          // :261-267
@@ -307,8 +369,13 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
         par ^= __float_as_uint(q);
       }
       m1v[i] = m1;
-      f1s[i] = opaque(xor_sign(cn_magnitude(p, m1), par));  // fold the row's sign parity in once
-      f2s[i] = opaque(xor_sign(cn_magnitude(p, m2), par));
+#if CCGPU_MS_CN_PAIR
+      const float2 g = cn_magnitude_pair(p, m1, m2);
+#else
+      const float2 g = make_float2(cn_magnitude(p, m1), cn_magnitude(p, m2));
+#endif
+      f1s[i] = opaque(xor_sign(g.x, par));  // fold the row's sign parity in once
+      f2s[i] = opaque(xor_sign(g.y, par));
     }
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
@@ -340,11 +407,19 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
             off -= N;
             wrapped = true;
           }
-          if (rvalid[i] && wrapped == (pass == 1)) yrow[i][SOFF + off] = __fadd_rn(yrow[i][SOFF + off], r[i][j]);
+          if (rvalid[i] && wrapped == (pass == 1)) {
+            if (VOLCS) {
+              volatile float *sp = yrow[i] + SOFF + off;
+              *sp = __fadd_rn(*sp, r[i][j]);
+            } else {
+              yrow[i][SOFF + off] = __fadd_rn(yrow[i][SOFF + off], r[i][j]);
+            }
+          }
         }
-        __syncwarp();  // required: without it the next step's loads overtake this step's stores (measured)
+        if (!VOLCS) __syncwarp();  // without it ptxas lets the next step's loads overtake this step's stores (measured)
       }
     }
+    if (VOLCS) __syncwarp();
 
     // ============ totals, hard decision (:178-183), stop test (:79-84)
     unsigned bw[NP];

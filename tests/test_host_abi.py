@@ -96,3 +96,17 @@ def test_h_alt(name, catalogue, golden_codes):
     assert not ((c.H().astype(np.int64) @ words.T.astype(np.int64)) % 2).any()
     if name == "bch_63_45":  # the reference's H_alt violates 254 of 810 checks for (63,45)
         assert int(((c.H_alt(as_reference=True).astype(np.int64) @ words.T.astype(np.int64)) % 2).sum()) == 254
+
+
+def test_no_packed_fma_in_library():
+    """The min-sum kernels must round every product and sum separately.  ptxas was seen to
+    contract a packed mul.rn.f32x2 + add.rn.f32x2 pair into FFMA2 despite the .rn qualifiers (the 2-D normalised
+    variant then differs from the reference in the last bit); guard the built library against that."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "FFMA2" not in sass and "FMUL2" not in sass
+    assert "FADD2" in sass  # the packed variable-node adds of ms_cyclic.cuh
