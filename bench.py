@@ -46,6 +46,19 @@ def measured_traffic_per_frame():
         return None
 
 
+def measured_sm_work_per_frame():
+    """(shared-memory wavefronts, warp instructions) per frame of the decode kernel at 4 dB, from the same capture"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ms_cyclic_63_36.json")) as f:
+            d = json.load(f)[0]
+        fr = float(d["frames_per_launch"])
+        wf = [v for k, v in d.items() if k.startswith("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")][0]
+        ins = [v for k, v in d.items() if k.startswith("smsp__inst_executed.sum")][0]
+        return float(wf) / fr, float(ins) / fr
+    except Exception:
+        return 998.0, 3976.0
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -291,6 +304,7 @@ def main():
         achieved = B * ALGO_BYTES_PER_FRAME / (kernel_ms * 1e-3) / 1e9
         lane_ops = iters_exec * (11 * EDGES + 2 * N)
         alu_peak = 148 * 128 * sm_max * 1e6
+        wf_frame, ins_frame = measured_sm_work_per_frame()
         line = {
             "metric": "decoded frames/s, BCH(63,36) normalised min-sum", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": kernel_ms,
@@ -319,12 +333,14 @@ def main():
             "alu": {"model": "avg_iters*(11E+2n) lane-ops/frame (SURVEY 8d)", "lane_ops_per_frame": lane_ops,
                     "achieved_lane_ops_per_s": value / world * lane_ops, "peak_lane_ops_per_s": alu_peak,
                     "frac": value / world * lane_ops / alu_peak},
-            # the pipe that actually binds (ncu: LSU 82.5 %, issue 83 %): 79 shared-memory wavefronts per
-            # frame-iteration (36 VN/CN loads, 36 column-sum read-modify-writes, 7 column phase) against one
-            # wavefront per SM per cycle
-            "smem": {"wavefronts_per_frame_iteration": 79, "achieved_wavefronts_per_s": value / world * iters_exec * 79,
+            # the pipes that actually bind (ncu, profiles/r1_ms_cyclic_63_36.txt: issue 79 %, ALU 79 %, LSU 80 %):
+            # shared-memory wavefronts against one per SM per cycle, warp instructions against four per SM per cycle;
+            # the per-frame counts come from the committed ncu capture of this kernel at the same Eb/N0
+            "smem": {"wavefronts_per_frame": wf_frame, "achieved_wavefronts_per_s": value / world * wf_frame,
                      "peak_wavefronts_per_s": 148 * sm_max * 1e6,
-                     "frac": value / world * iters_exec * 79 / (148 * sm_max * 1e6)},
+                     "frac": value / world * wf_frame / (148 * sm_max * 1e6)},
+            "issue": {"warp_instructions_per_frame": ins_frame, "achieved_per_s": value / world * ins_frame,
+                      "peak_per_s": 4 * 148 * sm_max * 1e6, "frac": value / world * ins_frame / (4 * 148 * sm_max * 1e6)},
             "clocks": clocks,
         }
         if not args.no_cpu:

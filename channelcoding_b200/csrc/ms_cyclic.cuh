@@ -37,8 +37,15 @@
 #include "ms_params.h"
 #include "ms_shape.h"
 
-#ifndef CCGPU_MS_YREG
-#define CCGPU_MS_YREG 0  /* measured: +18 registers cost more occupancy than the saved LDS gains (profiles/r1_notes.md) */
+#ifndef CCGPU_MS_YREG_N
+#define CCGPU_MS_YREG_N 10  /* y of the first N taps of a row stays in registers (one-row-per-lane shapes), see YN; \
+                               measured on BCH(63,36): 0 -> 2.25e8, 6 -> 2.28e8, 10 -> 2.30e8, 18 -> 2.26e8 frames/s */
+#endif
+#ifndef CCGPU_MS_MINBLK
+#define CCGPU_MS_MINBLK 8  /* resident CTAs per SM the small shapes are compiled for (64 registers) */
+#endif
+#ifndef CCGPU_MS_SMEM_COUNTERS
+#define CCGPU_MS_SMEM_COUNTERS 1  /* the six per-warp statistics live in shared memory, not in registers */
 #endif
 
 #ifndef CCGPU_MS_PACK2
@@ -113,16 +120,17 @@ __device__ __forceinline__ unsigned long long binom(unsigned n, unsigned r) {
 
 // resident CTAs per SM the register allocation aims at: 8 (64 registers) while the row's messages fit
 template <class S, int VN> constexpr int ms_min_blocks() {
-  return (S::RPL * S::W * ((VN == VN_SC || VN == VN_SPA) ? 2 : 1) + (CCGPU_MS_YREG && VN != VN_SC && !S::WRAP ? S::RPL * S::W : 0) <= 36) ? 8 : 1;
+  return (S::RPL * S::W * ((VN == VN_SC || VN == VN_SPA) ? 2 : 1) <= 36) ? CCGPU_MS_MINBLK : 1;
 }
 
 template <class S, int VN>
 __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_kernel(const __grid_constant__ MsParams p) {
   constexpr int N = S::N, W = S::W, RPL = S::RPL, NP = S::NP, FPW = S::FPW;
   constexpr bool WRAP = S::WRAP, SC = VN == VN_SC, SPA = VN == VN_SPA;
-  // y of the row's W edges is loop invariant: keep it in registers when the budget allows (saves one
-  // shared-memory load per edge and iteration)
-  constexpr bool YREG = CCGPU_MS_YREG && !SC && !WRAP && RPL * W <= 32;
+  // y of a row's edges is loop invariant: the first YN of them stay in registers (one shared-memory load less per
+  // edge and iteration) as far as the 64-register budget of 8 resident CTAs per SM allows
+  constexpr int YN = (!SC && !SPA && !WRAP && RPL == 1) ? (CCGPU_MS_YREG_N < W ? CCGPU_MS_YREG_N : W) : 0;
+  constexpr bool YREG = YN > 0;
   // ordered column sums: with one row per lane the read-modify-write chain goes through VOLATILE accesses, which
   // ptxas keeps in program order, instead of one __syncwarp per tap (ptxas proves the warp converged and turns
   // each of those into a NOP issue slot; measured +5 % on BCH(63,36)).  Two or more rows per lane keep the
@@ -212,9 +220,16 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
   int it = 0;
   float r[RPL][W];
   float qold[(SC || SPA) ? RPL : 1][(SC || SPA) ? W : 1];  // previous q (SCMS) / prefix products (SPA)
-  float yreg[YREG ? RPL : 1][YREG ? W : 1];
+  float yreg[RPL][YN > 0 ? YN : 1];
   // 32-bit per-warp counters (a warp sees far fewer than 2^32 / 50 frames per launch); widened at the end
+#if CCGPU_MS_SMEM_COUNTERS
+  // every thread owns one slot per statistic (only lead lanes ever write): six registers freed for the decoder
+  __shared__ unsigned cnt_s[6][kMsThreads];
+#pragma unroll
+  for (int s = 0; s < 6; ++s) cnt_s[s][threadIdx.x] = 0u;
+#else
   unsigned cnt_frames = 0, cnt_ferr = 0, cnt_berr = 0, cnt_iter = 0, cnt_fail = 0, cnt_und = 0;
+#endif
   constexpr int NBLK = (N + 3) >> 2;
 
   while (true) {
@@ -287,7 +302,7 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
 #pragma unroll
         for (int i = 0; i < RPL; ++i)
 #pragma unroll
-          for (int j = 0; j < W; ++j) yreg[i][j] = yrow[i][T::get(j)];
+          for (int j = 0; j < YN; ++j) yreg[i][j] = yrow[i][T::get(j)];
       }
     }
 
@@ -338,7 +353,8 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
           e0 = __fmul_rn(p.beta_f, e0);  // mul.rn.f32x2 + add.rn.f32x2 pair into FFMA2 (one rounding), which
           e1 = __fmul_rn(p.beta_f, e1);  // the reference does not do
         }
-        add2_rn(e0, e1, YREG ? yreg[i][j] : yrow[i][off0], YREG ? yreg[i][j + 1] : yrow[i][off1], qv[j], qv[j + 1]);
+        add2_rn(e0, e1, j < YN ? yreg[i][j < YN ? j : 0] : yrow[i][off0], j + 1 < YN ? yreg[i][j + 1 < YN ? j + 1 : 0] : yrow[i][off1],
+                qv[j], qv[j + 1]);
       }
 #pragma unroll
       for (int j = WP; j < W; ++j) {
@@ -346,7 +362,7 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
         if (WRAP && row[i] + off >= N) off -= N;
         float e = __fsub_rn(yrow[i][SOFF + off], r[i][j]);
         if (VN == VN_2D) e = __fmul_rn(p.beta_f, e);
-        qv[j] = __fadd_rn(e, YREG ? yreg[i][j] : yrow[i][off]);
+        qv[j] = __fadd_rn(e, j < YN ? yreg[i][j < YN ? j : 0] : yrow[i][off]);
       }
 #pragma unroll
       for (int j = 0; j < W; ++j) {
@@ -477,12 +493,21 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
         if (is_lead) {
           if (p.iter) p.iter[my_frame] = static_cast<uint8_t>(failed ? p.max_iter : it);
           if (p.failed) p.failed[my_frame] = failed ? 1 : 0;
+#if CCGPU_MS_SMEM_COUNTERS
+          cnt_s[0][threadIdx.x] += 1u;
+          cnt_s[1][threadIdx.x] += (failed || nbits != 0) ? 1u : 0u;
+          cnt_s[2][threadIdx.x] += static_cast<unsigned>(nbits);
+          cnt_s[3][threadIdx.x] += static_cast<unsigned>(it + 1);
+          cnt_s[4][threadIdx.x] += failed ? 1u : 0u;
+          cnt_s[5][threadIdx.x] += (!failed && nbits != 0) ? 1u : 0u;
+#else
           cnt_frames += 1;
           cnt_iter += static_cast<unsigned>(it + 1);
           cnt_fail += failed ? 1 : 0;
           cnt_berr += static_cast<unsigned>(nbits);
           cnt_ferr += (failed || nbits != 0) ? 1 : 0;
           cnt_und += (!failed && nbits != 0) ? 1 : 0;
+#endif
           next = units + static_cast<long long>(atomicAdd(p.work, 1ull));  // dynamic schedule
         }
       }
@@ -498,7 +523,13 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
 
   // ---------------- counters: warp reduce, one atomic per slot per warp
   if (p.counters != nullptr) {
+#if CCGPU_MS_SMEM_COUNTERS
+    unsigned long long v[6];
+#pragma unroll
+    for (int s = 0; s < 6; ++s) v[s] = cnt_s[s][threadIdx.x];
+#else
     unsigned long long v[6] = { cnt_frames, cnt_ferr, cnt_berr, cnt_iter, cnt_fail, cnt_und };  // widen
+#endif
 #pragma unroll
     for (int s = 0; s < 6; ++s) {
       unsigned long long x = v[s];
