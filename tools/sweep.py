@@ -47,6 +47,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ["NCCL_DEBUG"] = os.environ.get("CCGPU_NCCL_DEBUG", "WARN")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL logs to stdout by default: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = cc.Context(local)
     ctx.use_torch_stream()
