@@ -37,9 +37,12 @@
 #include "ms_params.h"
 #include "ms_shape.h"
 
-#ifndef CCGPU_MS_YREG_N
-#define CCGPU_MS_YREG_N 10  /* y of the first N taps of a row stays in registers (one-row-per-lane shapes), see YN; \
-                               measured on BCH(63,36): 0 -> 2.25e8, 6 -> 2.28e8, 10 -> 2.30e8, 18 -> 2.26e8 frames/s */
+#ifndef CCGPU_MS_YREG_BUDGET
+#define CCGPU_MS_YREG_BUDGET 28  /* messages + y values a lane keeps in registers (one-row-per-lane shapes), see YN; \
+   measured on BCH(63,36), W = 18: y of 0 / 6 / 10 / 18 taps -> 2.25e8 / 2.28e8 / 2.30e8 / 2.26e8 frames/s */
+#endif
+#ifndef CCGPU_MS_CAP_W
+#define CCGPU_MS_CAP_W 30  /* message registers per lane up to which the 64-register cap is applied */
 #endif
 #ifndef CCGPU_MS_MINBLK
 #define CCGPU_MS_MINBLK 8  /* resident CTAs per SM the small shapes are compiled for (64 registers) */
@@ -120,7 +123,9 @@ __device__ __forceinline__ unsigned long long binom(unsigned n, unsigned r) {
 
 // resident CTAs per SM the register allocation aims at: 8 (64 registers) while the row's messages fit
 template <class S, int VN> constexpr int ms_min_blocks() {
-  return (S::RPL * S::W * ((VN == VN_SC || VN == VN_SPA) ? 2 : 1) <= 36) ? CCGPU_MS_MINBLK : 1;
+  // measured: BCH(63,57), 32 messages per lane, 4.58e8 capped (spills) vs 4.82e8 free; self-correcting BCH(63,36),
+  // 2 x 18 values per lane, 1.71e8 capped vs 1.42e8 free
+  return ((VN == VN_SC || VN == VN_SPA) ? S::RPL * S::W <= 18 : S::RPL * S::W <= CCGPU_MS_CAP_W) ? CCGPU_MS_MINBLK : 1;
 }
 
 template <class S, int VN>
@@ -129,7 +134,8 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
   constexpr bool WRAP = S::WRAP, SC = VN == VN_SC, SPA = VN == VN_SPA;
   // y of a row's edges is loop invariant: the first YN of them stay in registers (one shared-memory load less per
   // edge and iteration) as far as the 64-register budget of 8 resident CTAs per SM allows
-  constexpr int YN = (!SC && !SPA && !WRAP && RPL == 1) ? (CCGPU_MS_YREG_N < W ? CCGPU_MS_YREG_N : W) : 0;
+  constexpr int YCAP = CCGPU_MS_YREG_BUDGET - W;
+  constexpr int YN = (!SC && !SPA && !WRAP && RPL == 1 && YCAP > 0) ? ((YCAP < W ? YCAP : W) & ~1) : 0;
   constexpr bool YREG = YN > 0;
   // ordered column sums: with one row per lane the read-modify-write chain goes through VOLATILE accesses, which
   // ptxas keeps in program order, instead of one __syncwarp per tap (ptxas proves the warp converged and turns
