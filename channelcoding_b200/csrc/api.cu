@@ -113,33 +113,48 @@ int ensure_stage(ccgpu_ctx *ctx, size_t bytes) {
 }
 
 // K1: one thread = one Philox block = four consecutive symbols of one frame.  The tile of
-// kTileFrames frames is assembled in shared memory and leaves the SM as coalesced 16-byte stores.
+// tile_frames frames is assembled in shared memory and leaves the SM as coalesced 16-byte streaming stores.
+// Tiles are handed out by a grid-stride loop over a grid of exactly the resident CTAs; the block -> (frame, block)
+// split uses a host-computed reciprocal (no integer division), the Philox round keys come from the constant bank.
 constexpr int kAwgnThreads = 256;
-__global__ void __launch_bounds__(kAwgnThreads) awgn_llr_kernel(float *__restrict__ y, uint32_t n, float sigma,
-                                                               uint64_t seed, uint32_t point, uint64_t frame0,
-                                                               uint64_t frames, uint32_t tile_frames) {
+struct AwgnParams {
+  float *y;
+  uint64_t frame0, frames;
+  uint32_t n, nblk, nblk_magic, tile_frames, point;
+  float sigma;
+  PhiloxKeys keys;
+};
+__global__ void __launch_bounds__(kAwgnThreads) awgn_llr_kernel(const __grid_constant__ AwgnParams p) {
   extern __shared__ float tile[];
-  const uint32_t nblk = (n + 3) >> 2;
-  const uint64_t tiles = (frames + tile_frames - 1) / tile_frames;
+  const uint32_t n = p.n, nblk = p.nblk;
+  const uint64_t tiles = (p.frames + p.tile_frames - 1) / p.tile_frames;
   for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
-    const uint64_t f0 = t * tile_frames;
-    const uint32_t nf = static_cast<uint32_t>(min(static_cast<uint64_t>(tile_frames), frames - f0));
+    const uint64_t f0 = t * p.tile_frames;
+    const uint32_t nf = static_cast<uint32_t>(min(static_cast<uint64_t>(p.tile_frames), p.frames - f0));
     for (uint32_t b = threadIdx.x; b < nf * nblk; b += blockDim.x) {
-      const uint32_t f = b / nblk, blk = b - f * nblk;
-      const float4 v = awgn_block(seed, point, frame0 + f0 + f, blk, sigma);
+      const uint32_t f = nblk == 1 ? b : __umulhi(b, p.nblk_magic);  // = b / nblk, exact for b * nblk < 2^32
+      const uint32_t blk = b - f * nblk;
+      const float4 v = awgn_block(p.keys, p.point, p.frame0 + f0 + f, blk, p.sigma);
       float *dst = tile + f * n + 4 * blk;
-      const float vv[4] = { v.x, v.y, v.z, v.w };
+      if (blk + 1 < nblk) {
+        dst[0] = v.x;
+        dst[1] = v.y;
+        dst[2] = v.z;
+        dst[3] = v.w;
+      } else {  // last block of the frame: n is not a multiple of four
+        const float vv[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
-      for (int e = 0; e < 4; ++e)
-        if (4 * blk + e < n) dst[e] = vv[e];
+        for (int e = 0; e < 4; ++e)
+          if (4 * blk + e < n) dst[e] = vv[e];
+      }
     }
     __syncthreads();
     const uint64_t base = f0 * n;              // multiple of 4 floats because tile_frames % 4 == 0
     const uint32_t total = nf * n;
-    float4 *out4 = reinterpret_cast<float4 *>(y + base);
+    float4 *out4 = reinterpret_cast<float4 *>(p.y + base);
     const float4 *in4 = reinterpret_cast<const float4 *>(tile);
     for (uint32_t i = threadIdx.x; i < total / 4; i += blockDim.x) __stcs(out4 + i, in4[i]);
-    for (uint32_t i = (total & ~3u) + threadIdx.x; i < total; i += blockDim.x) y[base + i] = tile[i];
+    for (uint32_t i = (total & ~3u) + threadIdx.x; i < total; i += blockDim.x) p.y[base + i] = tile[i];
     __syncthreads();
   }
 }
@@ -642,14 +657,25 @@ int ccgpu_awgn_llr(ccgpu_ctx *ctx, uint32_t n, double sigma, uint64_t seed, uint
     d_y = static_cast<float *>(ctx->d_stage);
   }
   if (reinterpret_cast<uintptr_t>(d_y) % 16 != 0) return fail(ctx, CCGPU_ERR_INVALID, "y must be 16-byte aligned");
-  // tile: a multiple of 4 frames (keeps every tile base 16-byte aligned), about 32 KB
-  uint32_t tile_frames = std::max<uint32_t>(4, (8192 / n) & ~3u);
-  const size_t smem = size_t(tile_frames) * n * sizeof(float);
-  const uint64_t tiles = (frames + tile_frames - 1) / tile_frames;
-  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, uint64_t(ctx->sm_count) * 8));
+  // tile: a multiple of 4 frames (keeps every tile base 16-byte aligned), about 16 KB: eight CTAs = 64 warps per SM
+  AwgnParams ap;
+  ap.y = d_y;
+  ap.frame0 = frame0;
+  ap.frames = frames;
+  ap.n = n;
+  ap.nblk = (n + 3) >> 2;
+  ap.nblk_magic = static_cast<uint32_t>(((uint64_t(1) << 32) + ap.nblk - 1) / ap.nblk);  // ceil(2^32 / nblk)
+  ap.tile_frames = std::max<uint32_t>(4, (4096 / n) & ~3u);
+  ap.point = point;
+  ap.sigma = static_cast<float>(sigma);
+  ap.keys = philox_round_keys(seed);
+  const size_t smem = size_t(ap.tile_frames) * n * sizeof(float);
+  const uint64_t tiles = (frames + ap.tile_frames - 1) / ap.tile_frames;
   CU(cudaFuncSetAttribute(awgn_llr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  awgn_llr_kernel<<<grid, kAwgnThreads, smem, ctx->stream>>>(d_y, n, static_cast<float>(sigma), seed, point, frame0,
-                                                            frames, tile_frames);
+  int resident = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, awgn_llr_kernel, kAwgnThreads, smem));
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, uint64_t(ctx->sm_count) * std::max(1, resident)));
+  awgn_llr_kernel<<<grid, kAwgnThreads, smem, ctx->stream>>>(ap);
   CU(cudaGetLastError());
   ctx->launches++;
   if (!dev) {

@@ -25,25 +25,64 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
-// two uniforms -> two N(0,1):  u in (0,1], v in [-pi,pi)  (MUFU lg2 / sin / cos)
+// Philox with the ten round keys precomputed on the host (they depend on the seed only): the rounds take their
+// key from the constant bank as a LOP3 operand instead of two uniform-datapath adds per round
+struct PhiloxKeys {
+  uint32_t x[10], y[10];
+};
+inline PhiloxKeys philox_round_keys(uint64_t seed) {
+  PhiloxKeys k;
+  uint32_t kx = static_cast<uint32_t>(seed), ky = static_cast<uint32_t>(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    k.x[r] = kx;
+    k.y[r] = ky;
+    kx += 0x9E3779B9u;
+    ky += 0xBB67AE85u;
+  }
+  return k;
+}
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &k) {
+#pragma unroll
+  for (int round = 0; round < 10; ++round) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x[round], lo1, hi0 ^ c.w ^ k.y[round], lo0);
+  }
+  return c;
+}
+
+// two uniforms -> two N(0,1):  u in (0,1], v in [-pi,pi).  Everything on the MUFU unit: lg2 / sqrt / sin / cos
+// (u >= 2^-33 is never subnormal, so the .ftz forms are exact equivalents and save the range fix-up; sqrt.approx(0) = 0
+// covers u == 1).  Relative error of a sample about 1e-6, far below the Monte-Carlo resolution; the CPU restatement
+// (oracle/channel_oracle.c, libm) is compared with a tolerance (tests/test_gpu_parity.py::test_channel_kernel).
 __device__ __forceinline__ float2 box_muller(uint32_t x0, uint32_t x1) {
   const float u = __fmaf_rn(static_cast<float>(x0), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
   const float v = static_cast<float>(static_cast<int32_t>(x1)) * 1.4629180792671596e-9f;
-  const float rad = sqrtf(-2.0f * __logf(u));
+  float lg, rad;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(lg * -1.3862943611198906f));  // -2 ln 2 * lg2 u = -2 ln u
   float s, c;
   __sincosf(v, &s, &c);
   return make_float2(rad * s, rad * c);
 }
 
 // the four channel values y = 1 + sigma * z of block `blk` of frame `frame`
-__device__ __forceinline__ float4 awgn_block(uint64_t seed, uint32_t point, uint64_t frame, uint32_t blk,
-                                             float sigma) {
-  const uint4 x = philox4x32_10(make_uint4(static_cast<uint32_t>(frame), static_cast<uint32_t>(frame >> 32), blk, point),
-                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+__device__ __forceinline__ float4 awgn_from_bits(const uint4 x, float sigma) {
   const float2 a = box_muller(x.x, x.y);
   const float2 b = box_muller(x.z, x.w);
-  return make_float4(__fadd_rn(1.0f, __fmul_rn(sigma, a.x)), __fadd_rn(1.0f, __fmul_rn(sigma, a.y)),
-                     __fadd_rn(1.0f, __fmul_rn(sigma, b.x)), __fadd_rn(1.0f, __fmul_rn(sigma, b.y)));
+  return make_float4(__fmaf_rn(sigma, a.x, 1.0f), __fmaf_rn(sigma, a.y, 1.0f), __fmaf_rn(sigma, b.x, 1.0f),
+                     __fmaf_rn(sigma, b.y, 1.0f));
+}
+__device__ __forceinline__ float4 awgn_block(uint64_t seed, uint32_t point, uint64_t frame, uint32_t blk,
+                                             float sigma) {
+  return awgn_from_bits(philox4x32_10(make_uint4(static_cast<uint32_t>(frame), static_cast<uint32_t>(frame >> 32), blk, point),
+                                      make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32))),
+                        sigma);
+}
+__device__ __forceinline__ float4 awgn_block(const PhiloxKeys &keys, uint32_t point, uint64_t frame, uint32_t blk,
+                                             float sigma) {
+  return awgn_from_bits(philox4x32_10(make_uint4(static_cast<uint32_t>(frame), static_cast<uint32_t>(frame >> 32), blk, point), keys),
+                        sigma);
 }
 
 }  // namespace ccgpu

@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(S::THREADS) ms_cyclic_cta_kernel(const __grid_
           if (WRAP && row[i] + off >= N) off -= N;
           const float s = yrow[i][NPAD + off];
           const float yy = yrow[i][off];
-          float e = __fsub_rn(s, r[i][j]);
-          if (VN == VN_2D) e = __fmul_rn(p.beta_f, e);
+          float e = __fsub_rn(s, r[i][j]);  // scalar adds here: the packed FADD2 form of ms_cyclic.cuh needs aligned
+          if (VN == VN_2D) e = __fmul_rn(p.beta_f, e);  // register pairs and spills at this kernel's 128-register budget
           float q = __fadd_rn(e, yy);
           if (SC) {
             const float qo = qold[i][j];
@@ -134,8 +134,9 @@ __global__ void __launch_bounds__(S::THREADS) ms_cyclic_cta_kernel(const __grid_
           par ^= __float_as_uint(q);
         }
         m1v[i] = m1;
-        f1s[i] = xor_sign(cn_magnitude(p, m1), par);
-        f2s[i] = xor_sign(cn_magnitude(p, m2), par);
+        const float2 g = cn_magnitude_pair(p, m1, m2);
+        f1s[i] = xor_sign(g.x, par);
+        f2s[i] = xor_sign(g.y, par);
       }
 #pragma unroll
       for (int i = 0; i < RPL; ++i)
