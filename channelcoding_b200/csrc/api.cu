@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -324,7 +325,8 @@ int ccgpu_create(int device, ccgpu_ctx **out) {
     cudaGetLastError();
     return CCGPU_ERR_NO_DEVICE;
   }
-  ccgpu_ctx *ctx = new ccgpu_ctx();
+  ccgpu_ctx *ctx = new (std::nothrow) ccgpu_ctx();
+  if (!ctx) return CCGPU_ERR_CUDA;
   ctx->device = device;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
@@ -422,16 +424,20 @@ int ccgpu_code_from_dense(ccgpu_ctx *ctx, const uint8_t *H, uint32_t rows, uint3
   if (!out || !H || rows == 0 || cols == 0) return CCGPU_ERR_INVALID;
   std::unique_lock<std::mutex> g;
   if (ctx) g = std::unique_lock<std::mutex>(ctx->mu);
-  CodeSpec s;
-  s.family = 2;
-  s.n = cols;
-  s.rows = rows;
-  s.k = rows;
-  s.l = cols > rows ? cols - rows : 0;
-  s.rate = rate;
-  s.H.assign(H, H + size_t(rows) * cols);
-  for (auto &v : s.H) v = v ? 1 : 0;
-  return make_code(ctx, std::move(s), out);
+  try {  // the ABI never throws: allocation failures come back as an error code
+    CodeSpec s;
+    s.family = 2;
+    s.n = cols;
+    s.rows = rows;
+    s.k = rows;
+    s.l = cols > rows ? cols - rows : 0;
+    s.rate = rate;
+    s.H.assign(H, H + size_t(rows) * cols);
+    for (auto &v : s.H) v = v ? 1 : 0;
+    return make_code(ctx, std::move(s), out);
+  } catch (const std::exception &e) {
+    return ctx ? fail(ctx, CCGPU_ERR_INVALID, e.what()) : CCGPU_ERR_INVALID;
+  }
 }
 
 int ccgpu_code_set_rows(ccgpu_code *code, uint32_t rows) {
@@ -491,7 +497,11 @@ int ccgpu_code_get_info(const ccgpu_code *code, ccgpu_code_info *out) {
 
 int ccgpu_code_to_string(const ccgpu_code *code, const char *tag, char *buf, size_t cap) {
   if (!code || !buf || cap == 0) return CCGPU_ERR_INVALID;
-  std::snprintf(buf, cap, "%s", code->spec.to_string(tag ? tag : "").c_str());
+  try {
+    std::snprintf(buf, cap, "%s", code->spec.to_string(tag ? tag : "").c_str());
+  } catch (const std::exception &) {
+    return CCGPU_ERR_INVALID;
+  }
   return CCGPU_OK;
 }
 
@@ -503,10 +513,14 @@ int ccgpu_code_H(const ccgpu_code *code, uint8_t *out) {
 
 int ccgpu_code_H_alt(const ccgpu_code *code, int as_reference, uint8_t *out, uint32_t *rows) {
   if (!code || !rows || code->spec.family == 2) return CCGPU_ERR_INVALID;
-  unsigned r = 0;
-  const std::vector<uint8_t> M = code->spec.h_alt(as_reference != 0, &r);
-  *rows = r;
-  if (out) std::memcpy(out, M.data(), M.size());
+  try {
+    unsigned r = 0;
+    const std::vector<uint8_t> M = code->spec.h_alt(as_reference != 0, &r);
+    *rows = r;
+    if (out) std::memcpy(out, M.data(), M.size());
+  } catch (const std::exception &) {
+    return CCGPU_ERR_INVALID;
+  }
   return CCGPU_OK;
 }
 
