@@ -160,6 +160,116 @@ __global__ void __launch_bounds__(kAwgnThreads) awgn_llr_kernel(const __grid_con
   }
 }
 
+// K1 launch: frames x n channel values into a 16-byte aligned device buffer
+int launch_awgn(ccgpu_ctx *ctx, float *d_y, uint32_t n, float sigma, uint64_t seed, uint32_t point, uint64_t frame0,
+                uint64_t frames) {
+  if (frames == 0) return CCGPU_OK;
+  if (reinterpret_cast<uintptr_t>(d_y) % 16 != 0) return fail(ctx, CCGPU_ERR_INVALID, "y must be 16-byte aligned");
+  // tile: a multiple of 4 frames (keeps every tile base 16-byte aligned), about 16 KB: eight CTAs = 64 warps per SM
+  AwgnParams ap;
+  ap.y = d_y;
+  ap.frame0 = frame0;
+  ap.frames = frames;
+  ap.n = n;
+  ap.nblk = (n + 3) >> 2;
+  ap.nblk_magic = static_cast<uint32_t>(((uint64_t(1) << 32) + ap.nblk - 1) / ap.nblk);  // ceil(2^32 / nblk)
+  ap.tile_frames = std::max<uint32_t>(4, (4096 / n) & ~3u);
+  ap.point = point;
+  ap.sigma = sigma;
+  ap.keys = philox_round_keys(seed);
+  const size_t smem = size_t(ap.tile_frames) * n * sizeof(float);
+  const uint64_t tiles = (frames + ap.tile_frames - 1) / ap.tile_frames;
+  CU(cudaFuncSetAttribute(awgn_llr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  int resident = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, awgn_llr_kernel, kAwgnThreads, smem));
+  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, uint64_t(ctx->sm_count) * std::max(1, resident)));
+  awgn_llr_kernel<<<grid, kAwgnThreads, smem, ctx->stream>>>(ap);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  return CCGPU_OK;
+}
+
+// ---- multiple-bases decoding (extension, BASELINE config 3): the code is cyclic, so decoding the received word
+// rotated by s positions on H is decoding the word itself on H rotated by -s: B rotations = B parity-check
+// matrices ("bases") from one compiled kernel.  Candidates are rotated back and the best one is kept.
+__global__ void __launch_bounds__(256) mbbp_roll_kernel(const float *__restrict__ y, float *__restrict__ out,
+                                                        const uint32_t *__restrict__ shifts, uint32_t n, uint32_t nb,
+                                                        uint64_t frames) {
+  const uint64_t total = frames * nb * n;
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t fb = i / n;
+    const uint32_t c = static_cast<uint32_t>(i - fb * n);
+    const uint64_t f = fb / nb;
+    const uint32_t b = static_cast<uint32_t>(fb - f * nb);
+    uint32_t src = c + shifts[b];
+    if (src >= n) src -= n;
+    out[i] = y[f * n + src];  // y_b[c] = y[(c + s_b) mod n]
+  }
+}
+// one thread per frame: correlation sum_c y[c] (1 - 2 x[c]) of every candidate (float32, c ascending in the
+// un-rotated domain), the best converged candidate wins (ties: lowest base), if none converged the frame fails and
+// the best failed candidate is reported
+__global__ void __launch_bounds__(128) mbbp_select_kernel(const float *__restrict__ y, const uint8_t *__restrict__ bits_b,
+                                                          const uint8_t *__restrict__ iter_b,
+                                                          const uint8_t *__restrict__ failed_b,
+                                                          const uint32_t *__restrict__ shifts, uint32_t n, uint32_t nb,
+                                                          uint32_t max_iter, uint64_t frames, uint8_t *__restrict__ chosen,
+                                                          uint8_t *__restrict__ iter_out, uint8_t *__restrict__ failed_out,
+                                                          unsigned long long *counters) {
+  unsigned long long executed = 0;
+  for (uint64_t f = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; f < frames;
+       f += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    int best = -1;
+    bool best_ok = false;
+    float best_m = 0.0f;
+    for (uint32_t b = 0; b < nb; ++b) {
+      const bool ok = failed_b[f * nb + b] == 0;
+      executed += ok ? iter_b[f * nb + b] + 1u : max_iter;
+      const uint8_t *x = bits_b + (f * nb + b) * n;
+      const uint32_t s = shifts[b];
+      float m = 0.0f;
+      uint32_t src = n - s;  // candidate bit of un-rotated column c is x[(c - s) mod n]
+      if (src >= n) src -= n;
+      for (uint32_t c = 0; c < n; ++c) {
+        const float v = y[f * n + c];
+        m = __fadd_rn(m, x[src] ? -v : v);
+        if (++src == n) src = 0;
+      }
+      const bool better = best < 0 || (ok && !best_ok) || (ok == best_ok && m > best_m);
+      if (better) {
+        best = static_cast<int>(b);
+        best_ok = ok;
+        best_m = m;
+      }
+    }
+    chosen[f] = static_cast<uint8_t>(best);
+    failed_out[f] = best_ok ? 0 : 1;
+    if (iter_out) iter_out[f] = iter_b[f * nb + best];
+  }
+  if (counters != nullptr) {
+    for (int o = 16; o > 0; o >>= 1) executed += __shfl_xor_sync(0xffffffffu, executed, o);
+    if ((threadIdx.x & 31) == 0 && executed) atomicAdd(counters + C_ITER, executed);
+  }
+}
+__global__ void __launch_bounds__(256) mbbp_unroll_kernel(const uint8_t *__restrict__ bits_b, const float *__restrict__ L_b,
+                                                          const uint8_t *__restrict__ chosen,
+                                                          const uint32_t *__restrict__ shifts, uint32_t n, uint32_t nb,
+                                                          uint64_t frames, uint8_t *__restrict__ bits, float *__restrict__ L) {
+  const uint64_t total = frames * n;
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t f = i / n;
+    const uint32_t c = static_cast<uint32_t>(i - f * n);
+    const uint32_t b = chosen[f];
+    uint32_t src = c + n - shifts[b];
+    if (src >= n) src -= n;
+    const uint64_t at = (f * nb + b) * n + src;
+    bits[i] = bits_b[at];
+    if (L) L[i] = L_b[at];
+  }
+}
+
 bool columns_covered(const CodeSpec &s) {
   for (unsigned c = 0; c < s.n; ++c) {
     bool any = false;
@@ -307,6 +417,74 @@ int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsP
   if (rc == -3) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "parity-check matrix too large for the CSR kernel");
   if (rc != 0) return cuda_fail(ctx, cudaGetLastError(), "ms_csr_launch");
   ctx->launches++;
+  return CCGPU_OK;
+}
+
+
+// multiple-bases decoding of `frames` frames whose channel values are in device memory (d_y).  Work buffers come
+// from the stage arena starting at `arena`; outputs are device pointers (L / iter / chosen nullable); when
+// `counters` is given the Monte-Carlo statistics of the all-zero codeword are accumulated as well.
+size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
+size_t mbbp_work_bytes(size_t n, uint32_t nb, uint64_t frames, bool want_L) {
+  return align256(nb * frames * n * sizeof(float)) + (want_L ? align256(nb * frames * n * sizeof(float)) : 0) +
+         align256(nb * frames * n) + 2 * align256(nb * frames) + align256(nb * sizeof(uint32_t));
+}
+int mbbp_run(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, const uint32_t *shifts, uint32_t nb,
+             const float *d_y, uint64_t frames, char *arena, uint8_t *d_bits, float *d_L, uint8_t *d_iter,
+             uint8_t *d_failed, uint8_t *d_chosen, unsigned long long *counters) {
+  const size_t n = code->spec.n;
+  float *rolled = reinterpret_cast<float *>(arena);
+  arena += align256(nb * frames * n * sizeof(float));
+  float *L_b = nullptr;
+  if (d_L) {
+    L_b = reinterpret_cast<float *>(arena);
+    arena += align256(nb * frames * n * sizeof(float));
+  }
+  uint8_t *bits_b = reinterpret_cast<uint8_t *>(arena);
+  arena += align256(nb * frames * n);
+  uint8_t *iter_b = reinterpret_cast<uint8_t *>(arena);
+  arena += align256(nb * frames);
+  uint8_t *failed_b = reinterpret_cast<uint8_t *>(arena);
+  arena += align256(nb * frames);
+  uint32_t *d_shifts = reinterpret_cast<uint32_t *>(arena);
+  CU(cudaMemcpyAsync(d_shifts, shifts, nb * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  const unsigned wide = static_cast<unsigned>(std::min<uint64_t>((nb * frames * n + 255) / 256, uint64_t(ctx->sm_count) * 16));
+  mbbp_roll_kernel<<<std::max(1u, wide), 256, 0, ctx->stream>>>(d_y, rolled, d_shifts, static_cast<uint32_t>(n), nb, frames);
+  CU(cudaGetLastError());
+  MsParams mp{};
+  fill_decoder(mp, code, params);
+  mp.src = SRC_HBM;
+  mp.frames = nb * frames;
+  mp.y = rolled;
+  mp.bits = bits_b;
+  mp.L = L_b;
+  mp.iter = iter_b;
+  mp.failed = failed_b;
+  const int rc = launch_ms(ctx, code, params, mp);
+  if (rc) return rc;
+  const unsigned per_frame = static_cast<unsigned>(std::min<uint64_t>((frames + 127) / 128, uint64_t(ctx->sm_count) * 16));
+  mbbp_select_kernel<<<std::max(1u, per_frame), 128, 0, ctx->stream>>>(d_y, bits_b, iter_b, failed_b, d_shifts,
+                                                                      static_cast<uint32_t>(n), nb, params->max_iter, frames,
+                                                                      d_chosen, d_iter, d_failed, counters);
+  CU(cudaGetLastError());
+  const unsigned narrow = static_cast<unsigned>(std::min<uint64_t>((frames * n + 255) / 256, uint64_t(ctx->sm_count) * 16));
+  mbbp_unroll_kernel<<<std::max(1u, narrow), 256, 0, ctx->stream>>>(bits_b, L_b, d_chosen, d_shifts, static_cast<uint32_t>(n), nb,
+                                                                    frames, d_bits, d_L);
+  CU(cudaGetLastError());
+  ctx->launches += 3;
+  if (counters) {
+    count_words_kernel<<<static_cast<unsigned>(std::min<uint64_t>((frames + 7) / 8, uint64_t(ctx->sm_count) * 8)), 256, 0,
+                         ctx->stream>>>(d_bits, d_failed, static_cast<uint32_t>(n), frames, counters);
+    CU(cudaGetLastError());
+    ctx->launches++;
+  }
+  return CCGPU_OK;
+}
+int check_bases(ccgpu_ctx *ctx, const ccgpu_code *code, const uint32_t *shifts, uint32_t nb) {
+  if (!shifts || nb == 0 || nb > 64) return fail(ctx, CCGPU_ERR_INVALID, "1..64 bases");
+  if (code->spec.family != 0) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "multiple-bases decoding needs a cyclic (BCH) code");
+  for (uint32_t b = 0; b < nb; ++b)
+    if (shifts[b] >= code->spec.n) return fail(ctx, CCGPU_ERR_INVALID, "rotation must be below n");
   return CCGPU_OK;
 }
 
@@ -670,28 +848,8 @@ int ccgpu_awgn_llr(ccgpu_ctx *ctx, uint32_t n, double sigma, uint64_t seed, uint
     if (rc) return rc;
     d_y = static_cast<float *>(ctx->d_stage);
   }
-  if (reinterpret_cast<uintptr_t>(d_y) % 16 != 0) return fail(ctx, CCGPU_ERR_INVALID, "y must be 16-byte aligned");
-  // tile: a multiple of 4 frames (keeps every tile base 16-byte aligned), about 16 KB: eight CTAs = 64 warps per SM
-  AwgnParams ap;
-  ap.y = d_y;
-  ap.frame0 = frame0;
-  ap.frames = frames;
-  ap.n = n;
-  ap.nblk = (n + 3) >> 2;
-  ap.nblk_magic = static_cast<uint32_t>(((uint64_t(1) << 32) + ap.nblk - 1) / ap.nblk);  // ceil(2^32 / nblk)
-  ap.tile_frames = std::max<uint32_t>(4, (4096 / n) & ~3u);
-  ap.point = point;
-  ap.sigma = static_cast<float>(sigma);
-  ap.keys = philox_round_keys(seed);
-  const size_t smem = size_t(ap.tile_frames) * n * sizeof(float);
-  const uint64_t tiles = (frames + ap.tile_frames - 1) / ap.tile_frames;
-  CU(cudaFuncSetAttribute(awgn_llr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  int resident = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, awgn_llr_kernel, kAwgnThreads, smem));
-  const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, uint64_t(ctx->sm_count) * std::max(1, resident)));
-  awgn_llr_kernel<<<grid, kAwgnThreads, smem, ctx->stream>>>(ap);
-  CU(cudaGetLastError());
-  ctx->launches++;
+  const int rc = launch_awgn(ctx, d_y, n, static_cast<float>(sigma), seed, point, frame0, frames);
+  if (rc) return rc;
   if (!dev) {
     CU(cudaMemcpyAsync(y, d_y, frames * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -736,6 +894,102 @@ int ccgpu_awgn_point(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_para
   mp.frame0 = frame0;
   mp.frames = frames;
   return counted_launch(ctx, code, params, mp, out);
+}
+
+int ccgpu_decode_llr_mbbp(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, const uint32_t *shifts,
+                          uint32_t n_bases, const float *y, uint64_t frames, uint8_t *bits, float *L, uint8_t *iter,
+                          uint8_t *failed, uint8_t *chosen) {
+  if (!ctx || !code || !y || !bits || !failed) return fail(ctx, CCGPU_ERR_INVALID, "null argument");
+  if (code->ctx != ctx) return fail(ctx, CCGPU_ERR_INVALID, "code was not created on this context");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  int rc = check_params(ctx, params);
+  if (rc) return rc;
+  rc = check_bases(ctx, code, shifts, n_bases);
+  if (rc) return rc;
+  if (frames == 0) return CCGPU_OK;
+  CU(cudaSetDevice(ctx->device));
+  const size_t n = code->spec.n;
+  const bool dev = is_device_ptr(y);
+  if (dev && (!is_device_ptr(bits) || !is_device_ptr(failed) || (L && !is_device_ptr(L)) || (iter && !is_device_ptr(iter)) ||
+              (chosen && !is_device_ptr(chosen))))
+    return fail(ctx, CCGPU_ERR_INVALID, "y is a device pointer: every output must be one too");
+  // chunks bound the work arena (all candidates of a chunk are decoded in one launch)
+  const size_t per_frame = mbbp_work_bytes(n, n_bases, 1, L != nullptr) / 1 + n * (sizeof(float) * 2 + 1) + 3;
+  const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(frames, (size_t(512) << 20) / per_frame));
+  const size_t io = align256(chunk * n * sizeof(float)) * 2 + align256(chunk * n) + 3 * align256(chunk);
+  rc = ensure_stage(ctx, io + mbbp_work_bytes(n, n_bases, chunk, L != nullptr) + 4096);
+  if (rc) return rc;
+  char *base = static_cast<char *>(ctx->d_stage);
+  float *s_y = reinterpret_cast<float *>(base);
+  float *s_L = reinterpret_cast<float *>(base + align256(chunk * n * sizeof(float)));
+  uint8_t *s_bits = reinterpret_cast<uint8_t *>(base + 2 * align256(chunk * n * sizeof(float)));
+  uint8_t *s_iter = s_bits + align256(chunk * n);
+  uint8_t *s_failed = s_iter + align256(chunk);
+  uint8_t *s_chosen = s_failed + align256(chunk);
+  char *arena = base + io;
+  for (uint64_t f0 = 0; f0 < frames; f0 += chunk) {
+    const uint64_t nf = std::min(chunk, frames - f0);
+    if (dev) {
+      rc = mbbp_run(ctx, code, params, shifts, n_bases, y + f0 * n, nf, arena, bits + f0 * n, L ? L + f0 * n : nullptr,
+                    iter ? iter + f0 : s_iter, failed + f0, chosen ? chosen + f0 : s_chosen, nullptr);
+      if (rc) return rc;
+    } else {
+      CU(cudaMemcpyAsync(s_y, y + f0 * n, nf * n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+      rc = mbbp_run(ctx, code, params, shifts, n_bases, s_y, nf, arena, s_bits, L ? s_L : nullptr, s_iter, s_failed, s_chosen,
+                    nullptr);
+      if (rc) return rc;
+      CU(cudaMemcpyAsync(bits + f0 * n, s_bits, nf * n, cudaMemcpyDeviceToHost, ctx->stream));
+      if (L) CU(cudaMemcpyAsync(L + f0 * n, s_L, nf * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+      if (iter) CU(cudaMemcpyAsync(iter + f0, s_iter, nf, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(failed + f0, s_failed, nf, cudaMemcpyDeviceToHost, ctx->stream));
+      if (chosen) CU(cudaMemcpyAsync(chosen + f0, s_chosen, nf, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));  // the staging buffers are reused by the next chunk
+    }
+  }
+  return CCGPU_OK;
+}
+
+int ccgpu_awgn_point_mbbp(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, const uint32_t *shifts,
+                          uint32_t n_bases, double ebno_db, uint64_t seed, uint32_t point, uint64_t frame0, uint64_t frames,
+                          ccgpu_counters *out) {
+  if (!ctx || !code || !out) return fail(ctx, CCGPU_ERR_INVALID, "null argument");
+  if (code->ctx != ctx) return fail(ctx, CCGPU_ERR_INVALID, "code was not created on this context");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  int rc = check_params(ctx, params);
+  if (rc) return rc;
+  rc = check_bases(ctx, code, shifts, n_bases);
+  if (rc) return rc;
+  CU(cudaSetDevice(ctx->device));
+  const size_t n = code->spec.n;
+  const bool dev = is_device_ptr(out);
+  unsigned long long *counters = dev ? reinterpret_cast<unsigned long long *>(out) : ctx->d_counters;
+  if (!dev) CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(ccgpu_counters), ctx->stream));
+  const size_t per_frame = mbbp_work_bytes(n, n_bases, 1, false) + n * (sizeof(float) + 1) + 3;
+  const uint64_t chunk = std::max<uint64_t>(4, std::min<uint64_t>(std::max<uint64_t>(frames, 4), (size_t(512) << 20) / per_frame) & ~uint64_t(3));
+  const size_t io = align256(chunk * n * sizeof(float)) + align256(chunk * n) + 3 * align256(chunk);
+  rc = ensure_stage(ctx, io + mbbp_work_bytes(n, n_bases, chunk, false) + 4096);
+  if (rc) return rc;
+  char *base = static_cast<char *>(ctx->d_stage);
+  float *s_y = reinterpret_cast<float *>(base);
+  uint8_t *s_bits = reinterpret_cast<uint8_t *>(base + align256(chunk * n * sizeof(float)));
+  uint8_t *s_iter = s_bits + align256(chunk * n);
+  uint8_t *s_failed = s_iter + align256(chunk);
+  uint8_t *s_chosen = s_failed + align256(chunk);
+  const float sigma = static_cast<float>(ccgpu_sigma(code->spec.rate, ebno_db));
+  if (params->variant == CCGPU_SPA) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "multiple-bases points take the min-sum variants");
+  for (uint64_t f0 = 0; f0 < frames; f0 += chunk) {
+    const uint64_t nf = std::min(chunk, frames - f0);
+    rc = launch_awgn(ctx, s_y, static_cast<uint32_t>(n), sigma, seed, point, frame0 + f0, nf);
+    if (rc) return rc;
+    rc = mbbp_run(ctx, code, params, shifts, n_bases, s_y, nf, base + io, s_bits, nullptr, s_iter, s_failed, s_chosen, counters);
+    if (rc) return rc;
+  }
+  if (!dev) {
+    CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(ccgpu_counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out = *ctx->h_counters;
+  }
+  return CCGPU_OK;
 }
 
 int ccgpu_bitflip_point(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, uint32_t weight,

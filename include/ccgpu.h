@@ -190,6 +190,29 @@ int ccgpu_awgn_llr(ccgpu_ctx *ctx, uint32_t n, double sigma, uint64_t seed, uint
 int ccgpu_awgn_point(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, double ebno_db,
                      uint64_t seed, uint32_t point, uint64_t frame0, uint64_t frames, ccgpu_counters *out);
 
+/* EXTENSION (no reference implementation; BASELINE.json config 3 "multiple-bases parity-check matrices (cyclic-shift
+ * rows)"): multiple-bases decoding.  The code is cyclic, so rotating the received word by s positions and decoding on
+ * H (codes/cyclic.h:346-359) is decoding the word itself on H rotated the other way: `n_bases` rotations shifts[b] < n
+ * give n_bases different parity-check matrices of the same code out of ONE kernel.  Every frame is decoded
+ * n_bases times (y_b[c] = y[(c + shifts[b]) mod n], all candidates in one launch of the min-sum kernel with the
+ * arithmetic of ccgpu_decode_llr), the candidates are rotated back, and the one with the largest correlation
+ * sum_c y[c] (1 - 2 x[c]) (float32, c ascending) among the converged candidates is returned (ties: lowest base);
+ * if none converged the frame is reported failed with the best non-converged candidate.  With n_bases = 1 and
+ * shifts[0] = 0 the result equals ccgpu_decode_llr.  `iter` is the iteration index of the returned candidate,
+ * `chosen` (nullable) the index of its base.  Pinned by tests/test_gpu_parity.py::test_mbbp_* against the CPU oracle
+ * run on the rotated words with the same selection rule.  Host or device pointers like ccgpu_decode_llr; binary
+ * BCH codes; use the GF(2) stop rule for non-zero codewords. */
+int ccgpu_decode_llr_mbbp(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, const uint32_t *shifts,
+                          uint32_t n_bases, const float *y, uint64_t frames, uint8_t *bits, float *L, uint8_t *iter,
+                          uint8_t *failed, uint8_t *chosen);
+
+/* one Eb/N0 point (frames [frame0, frame0 + frames) of the stream ccgpu_awgn_point draws) decoded with multiple
+ * bases: channel kernel -> rotations -> decode -> selection -> counters, everything on the device.  `iterations`
+ * counts the iterations executed over ALL bases (the work), the other counters refer to the returned word. */
+int ccgpu_awgn_point_mbbp(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, const uint32_t *shifts,
+                          uint32_t n_bases, double ebno_db, uint64_t seed, uint32_t point, uint64_t frame0, uint64_t frames,
+                          ccgpu_counters *out);
+
 /* the same Eb/N0 point for the HARD-decision tags (BM / PGZ / Euklid decoders of benchmark.c++:29-64 inside
  * awgn_simulation): channel, hard decision (codes/codes.h:43-52: bit = y < 0), algebraic decode
  * (cyclic.h:207-252) and the error test, all on the device; binary BCH codes.  iterations stays 0. */

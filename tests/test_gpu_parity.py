@@ -492,3 +492,89 @@ def test_edge_cases_and_errors(ctx, catalogue):
     with pytest.raises(cc.CcgpuError) as ei:
         dense.gf_decode(np.zeros((1, 63), np.uint8))
     assert ei.value.code == -3  # CCGPU_ERR_UNSUPPORTED: no field / roots behind a dense matrix
+
+
+# ---------------------------------------------------------------------------------------------------
+# multiple-bases decoding (extension, include/ccgpu.h ccgpu_decode_llr_mbbp)
+def mbbp_restatement(H, y, shifts, variant, alpha, beta, max_iter, stop_rule):
+    """the definition in include/ccgpu.h on the CPU: oracle decode of every rotation, rotate back, float32 correlation
+    accumulated column by column, best converged candidate (ties: lowest base), else best failed candidate"""
+    frames, n = y.shape
+    cands = []
+    for s in shifts:
+        b, L, it, failed = oracle.min_sum(H, np.roll(y, -int(s), axis=1), variant, alpha, beta, max_iter, stop_rule)
+        x = np.roll(b, int(s), axis=1)
+        m = np.cumsum(np.where(x != 0, -y, y).astype(np.float32), axis=1, dtype=np.float32)[:, -1]
+        cands.append((x, np.roll(L, int(s), axis=1), it, failed, m))
+    bits = np.empty((frames, n), np.uint8)
+    Lout = np.empty((frames, n), np.float32)
+    it_out = np.empty(frames, np.uint32)
+    failed_out = np.empty(frames, np.uint8)
+    chosen = np.empty(frames, np.uint8)
+    for f in range(frames):
+        best = None
+        for bi, (x, L, it, failed, m) in enumerate(cands):
+            ok = failed[f] == 0
+            if best is None or (ok and not best[1]) or (ok == best[1] and m[f] > best[2]):
+                best = (bi, ok, m[f])
+        bi = best[0]
+        bits[f], Lout[f], it_out[f], failed_out[f], chosen[f] = cands[bi][0][f], cands[bi][1][f], cands[bi][2][f], 0 if best[1] else 1, bi
+    return bits, Lout, it_out, failed_out, chosen
+
+
+def test_mbbp_single_base_is_plain(ctx, catalogue):
+    code = make_code(ctx, catalogue["bch_63_36"])
+    rng = np.random.default_rng(41)
+    y = (1 + oracle.sigma(36 / 63, 3.0) * rng.standard_normal((4000, 63))).astype(np.float32)
+    plain = code.decode(y, "NMS", 0.8)
+    b, L, it, failed, chosen = code.decode_mbbp(y, [0], "NMS", 0.8)
+    assert_same((b, L, it, failed), plain, "one base, no rotation")
+    assert not chosen.any()
+
+
+@pytest.mark.parametrize("name,frames,ebno", [("bch_31_16", 1500, 3.0), ("bch_63_36", 800, 3.5), ("bch_127_64", 40, 4.0)])
+def test_mbbp_matches_restatement(ctx, name, frames, ebno, catalogue):
+    """random codewords, GF(2) stop rule, four rotations: every output equals the CPU restatement built on the oracle"""
+    import torch
+    e = catalogue[name]
+    code = make_code(ctx, e)
+    n = e["n"]
+    rng = np.random.default_rng(zlib.crc32(("mbbp" + name).encode()))
+    words = code.encode(rng.integers(0, 2, size=(frames, e["l"])).astype(np.uint8))
+    y = ((1.0 - 2.0 * words) + oracle.sigma(e["rate"], ebno) * rng.standard_normal((frames, n))).astype(np.float32)
+    shifts = [0, 5, n // 2, n - 3]
+    for variant, alpha, beta, mi in (("NMS", 0.8, 0.0, 20), ("SCMS2", 1.0, 0.0, 15)):
+        ref = mbbp_restatement(code.H(), y, shifts, variant, alpha, beta, mi, 1)
+        got = code.decode_mbbp(y, shifts, variant, alpha, beta, mi, 1)
+        assert np.array_equal(got[4], ref[4]), (name, variant, "chosen base")
+        assert_same(got[:4], ref[:4], "%s %s multiple bases" % (name, variant))
+        # device pointers give the same
+        dev = code.decode_mbbp(torch.from_numpy(y).cuda(), shifts, variant, alpha, beta, mi, 1)
+        ctx.sync()
+        assert_same(tuple(t.cpu().numpy() for t in dev[:4]), ref[:4], "%s %s device path" % (name, variant))
+        # more bases never lose a frame the first base decodes to a codeword with a better metric; here: the
+        # multiple-bases word error rate is not worse than the single-base one
+        single = code.decode(y, variant, alpha, beta, mi, 1)
+        err_single = ((single[0] != words).any(axis=1) | (single[3] != 0)).mean()
+        err_multi = ((got[0] != words).any(axis=1) | (got[3] != 0)).mean()
+        assert err_multi <= err_single + 1e-9, (name, variant, err_single, err_multi)
+
+
+def test_mbbp_point(ctx, catalogue):
+    """fused point: counters equal channel kernel -> decode_mbbp -> host count, shards add up, and rotations help"""
+    import channelcoding_b200 as cc
+    code = make_code(ctx, catalogue["bch_63_36"])
+    frames, eb, shifts = 40000, 4.0, [0, 7, 19, 31, 44, 58]
+    c = code.awgn_point_mbbp(eb, frames, shifts, "NMS", 0.8, seed=5, point=2, frame0=64)
+    y = ctx.awgn_llr(63, np.float32(cc.sigma(code.rate, eb)), seed=5, point=2, frame0=64, frames=frames)
+    b, _, it, failed, _ = code.decode_mbbp(y, shifts, "NMS", 0.8, want_L=False)
+    nz = b.any(axis=1)
+    assert c["frames"] == frames and c["failures"] == int(failed.sum())
+    assert c["frame_errors"] == int((nz | (failed != 0)).sum()) and c["bit_errors"] == int(b.sum())
+    assert c["undetected"] == int((nz & (failed == 0)).sum())
+    halves = [code.awgn_point_mbbp(eb, frames // 2, shifts, "NMS", 0.8, seed=5, point=2, frame0=64 + i * (frames // 2)) for i in range(2)]
+    for k in ("frames", "frame_errors", "bit_errors", "iterations", "failures", "undetected"):
+        assert c[k] == halves[0][k] + halves[1][k], k
+    one = code.awgn_point(eb, frames, "NMS", 0.8, seed=5, point=2, frame0=64)
+    assert c["frame_errors"] < 0.8 * one["frame_errors"], (c, one)
+    assert c["iterations"] > one["iterations"]

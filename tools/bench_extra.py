@@ -75,6 +75,25 @@ def main():
     fused("BCH(127,64) NMS redundant H (127 rows)", c127, 4.0, int(2e6 * scale), "NMS", 0.8, stop=1, label=", redundant")
     c127.set_rows(63)
     fused("BCH(127,64) NMS gf2-stop", c127, 4.0, int(2e6 * scale), "NMS", 0.8, stop=1)
+    # multiple bases (extension): the same frames decoded on 1 / 4 / 8 / 16 rotations of H, best candidate kept
+    for eb in (4.0, 5.0):
+        for nb in (1, 4, 8, 16):
+            shifts = [(127 * i) // nb for i in range(nb)]
+            frames = int(1e6 * scale)
+            c127.awgn_point_mbbp(eb, frames, shifts, "NMS", 0.8, stop_rule=1)  # warm-up: also sizes the work arena
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            c = c127.awgn_point_mbbp(eb, frames, shifts, "NMS", 0.8, stop_rule=1, seed=1, point=7)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            print(json.dumps({"config": "BCH(127,64) NMS gf2-stop, %d bases (rotations of H)" % nb,
+                              "path": "awgn_point_mbbp (channel kernel -> rotate -> decode -> select -> count)",
+                              "ebno_db": eb, "variant": "NMS", "bases": nb, "frames": c["frames"],
+                              "frames_per_s": frames / (ms * 1e-3), "candidate_decodes_per_s": nb * frames / (ms * 1e-3),
+                              "ms": ms, "wer": c["frame_errors"] / frames, "ber": c["bit_errors"] / frames / 127,
+                              "undetected": c["undetected"], "avg_iterations_all_bases": c["iterations"] / frames}), flush=True)
     c255 = ctx.bch(8, errors=18)
     for eb in (4.0, 6.0):
         fused("BCH(255,131) NMS", c255, eb, int(2e5 * scale), "NMS", 0.8, refkey=(FAM_BCH, 8, CAP_ERRORS, 18, ALG_SOFT0 + 1))
