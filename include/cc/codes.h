@@ -214,6 +214,16 @@ public:
     const ccgpu_ms_params p = ms_params();
     h_->ctx->check(ccgpu_decode_llr(h_->ctx->get(), h_->code, &p, y, frames, bits, L, iter, failed));
   }
+  // ---- extension: multiple-bases decoding (ccgpu_decode_llr_mbbp): every frame is decoded on H rotated by each
+  // of `rotations` and the best converged candidate is kept; chosen[f] (optional) is the index of its rotation
+  void correct_batch_multiple_bases(const float *y, uint64_t frames, const std::vector<uint32_t> &rotations, uint8_t *bits,
+                                    uint8_t *failed, uint8_t *iter = nullptr, float *L = nullptr,
+                                    uint8_t *chosen = nullptr) const {
+    static_assert(std::is_base_of<soft_decision_tag, Algorithm>::value, "soft-decision tag required");
+    const ccgpu_ms_params p = ms_params();
+    h_->ctx->check(ccgpu_decode_llr_mbbp(h_->ctx->get(), h_->code, &p, rotations.data(),
+                                         static_cast<uint32_t>(rotations.size()), y, frames, bits, L, iter, failed, chosen));
+  }
   // ---- batched algebraic decoding: count x n symbols
   void correct_batch(const uint8_t *words, uint64_t count, uint8_t *corrected, uint8_t *failed,
                      uint8_t *n_errors = nullptr) const {

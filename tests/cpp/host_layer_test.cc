@@ -184,6 +184,36 @@ static int gpu_tests(const std::string &dir) {
     CHECK(first == 1.0 && points == 15);  // 1.0, 1.5, .., 8.0
     CHECK(last_wer < 1e-3);
   }
+  // extension: multiple bases through the C++ layer -- one rotation 0 equals correct_batch, more rotations decode
+  // at least the frames the first one decodes
+  {
+    primitive_bch<6, errors<5>, normalized_min_sum_tag<50, std::ratio<8, 10> > > code;
+    const unsigned n = 63, frames = 3000;
+    std::vector<float> y(size_t(frames) * n);
+    uint64_t lcg = 12345;
+    for (auto &v : y) {  // crude noise, enough to make a good share of the frames fail on one matrix
+      float acc = 0;
+      for (int k = 0; k < 12; ++k) {
+        lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+        acc += float((lcg >> 40) & 0xffff) / 65536.0f;
+      }
+      v = 1.0f + 0.66f * (acc - 6.0f);
+    }
+    std::vector<uint8_t> b1(y.size()), f1(frames), b2(y.size()), f2(frames), b3(y.size()), f3(frames), chosen(frames);
+    code.correct_batch(y.data(), frames, b1.data(), f1.data());
+    code.correct_batch_multiple_bases(y.data(), frames, { 0u }, b2.data(), f2.data());
+    CHECK(b1 == b2 && f1 == f2);
+    code.correct_batch_multiple_bases(y.data(), frames, { 0u, 9u, 20u, 33u, 47u }, b3.data(), f3.data(), nullptr, nullptr,
+                                      chosen.data());
+    unsigned fail1 = 0, fail3 = 0, moved = 0;
+    for (unsigned f = 0; f < frames; ++f) {
+      fail1 += f1[f];
+      fail3 += f3[f];
+      moved += chosen[f] != 0;
+      if (!f1[f]) CHECK(!f3[f]);
+    }
+    CHECK(fail1 > 50 && fail3 < fail1 && moved > 0);
+  }
   std::cout << "gpu tests ok" << std::endl;
   return 0;
 }
