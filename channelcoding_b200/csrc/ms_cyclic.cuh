@@ -44,6 +44,10 @@
 #ifndef CCGPU_MS_CAP_W
 #define CCGPU_MS_CAP_W 30  /* message registers per lane up to which the 64-register cap is applied */
 #endif
+#ifndef CCGPU_MS_MID_MINBLK
+#define CCGPU_MS_MID_MINBLK 5  /* resident CTAs per SM asked for when a lane keeps 31..64 messages (102 registers): \
+   measured +2 % BCH(127,64), +8 % (127,106), +24 % (127,99), +10 % (127,113) over the unconstrained allocation; 6 spills */
+#endif
 #ifndef CCGPU_MS_MINBLK
 #define CCGPU_MS_MINBLK 8  /* resident CTAs per SM the small shapes are compiled for (64 registers) */
 #endif
@@ -125,7 +129,9 @@ __device__ __forceinline__ unsigned long long binom(unsigned n, unsigned r) {
 template <class S, int VN> constexpr int ms_min_blocks() {
   // measured: BCH(63,57), 32 messages per lane, 4.58e8 capped (spills) vs 4.82e8 free; self-correcting BCH(63,36),
   // 2 x 18 values per lane, 1.71e8 capped vs 1.42e8 free
-  return ((VN == VN_SC || VN == VN_SPA) ? S::RPL * S::W <= 18 : S::RPL * S::W <= CCGPU_MS_CAP_W) ? CCGPU_MS_MINBLK : 1;
+  return ((VN == VN_SC || VN == VN_SPA) ? S::RPL * S::W <= 18 : S::RPL * S::W <= CCGPU_MS_CAP_W) ? CCGPU_MS_MINBLK
+         : (VN == VN_PLAIN || VN == VN_2D) && S::RPL * S::W <= 64                                   ? CCGPU_MS_MID_MINBLK
+                                                                                                     : 1;
 }
 
 template <class S, int VN>
