@@ -18,10 +18,14 @@
 #include "ms_shape.h"
 #include "ms_shape_cta.h"
 
+#ifndef CCGPU_MS_CTA_MINBLK
+#define CCGPU_MS_CTA_MINBLK 1  /* measured: 5 CTAs per SM (96 registers, 108 bytes spilled) is 7 % slower than 4 (128 registers) */
+#endif
+
 namespace ccgpu {
 
 template <class S, int VN>
-__global__ void __launch_bounds__(S::THREADS) ms_cyclic_cta_kernel(const __grid_constant__ MsParams p) {
+__global__ void __launch_bounds__(S::THREADS, CCGPU_MS_CTA_MINBLK) ms_cyclic_cta_kernel(const __grid_constant__ MsParams p) {
   constexpr int N = S::N, W = S::W, RPL = S::RPL, NPW = S::NPW, THREADS = S::THREADS, CPASS = S::CPASS;
   constexpr bool WRAP = S::WRAP, SC = VN == VN_SC;
   constexpr int NPAD = NPW * 32;
