@@ -270,6 +270,48 @@ __global__ void __launch_bounds__(256) mbbp_unroll_kernel(const uint8_t *__restr
   }
 }
 
+// ---- binary BCH with erasures the way the reference's PGZ decoder does it (codes/bch.h:97-149): the erased positions
+// are filled with zeros, then with ones, both words are decoded errors-only, the success with fewer corrected
+// positions wins (ties: the zero fill, it is tried first)
+__global__ void __launch_bounds__(256) pgz_fill_kernel(const uint8_t *__restrict__ words, const uint8_t *__restrict__ epos,
+                                                       const uint8_t *__restrict__ ecnt, uint32_t me, uint32_t n,
+                                                       uint64_t count, uint8_t *__restrict__ out) {
+  const uint64_t total = count * n;
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t w = i / n;
+    const uint32_t c = static_cast<uint32_t>(i - w * n);
+    bool erased = false;
+    const uint32_t e = min(static_cast<uint32_t>(ecnt[w]), me);
+    for (uint32_t k = 0; k < e; ++k) erased |= epos[w * me + k] == c;
+    const uint8_t v = words[i];
+    out[(2 * w) * n + c] = erased ? 0 : v;
+    out[(2 * w + 1) * n + c] = erased ? 1 : v;
+  }
+}
+__global__ void __launch_bounds__(256) pgz_select_kernel(const uint8_t *__restrict__ words, const uint8_t *__restrict__ cand,
+                                                         const uint8_t *__restrict__ cand_ne,
+                                                         const uint8_t *__restrict__ cand_fail,
+                                                         const uint8_t *__restrict__ ecnt, uint32_t t, uint32_t n,
+                                                         uint64_t count, uint8_t *__restrict__ corrected,
+                                                         uint8_t *__restrict__ n_errors, uint8_t *__restrict__ failed) {
+  const uint64_t total = count * n;
+  for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    const uint64_t w = i / n;
+    const uint32_t c = static_cast<uint32_t>(i - w * n);
+    const bool ok0 = cand_fail[2 * w] == 0, ok1 = cand_fail[2 * w + 1] == 0;
+    const bool too_many = ecnt[w] > 2 * t;  // bch.h:104-106
+    const bool fail = too_many || (!ok0 && !ok1);
+    const int pick = (ok0 && (!ok1 || cand_ne[2 * w] <= cand_ne[2 * w + 1])) ? 0 : 1;
+    corrected[i] = fail ? words[i] : cand[(2 * w + pick) * n + c];
+    if (c == 0) {
+      failed[w] = fail ? 1 : 0;
+      if (n_errors) n_errors[w] = fail ? 0 : cand_ne[2 * w + pick];
+    }
+  }
+}
+
 bool columns_covered(const CodeSpec &s) {
   for (unsigned c = 0; c < s.n; ++c) {
     bool any = false;
@@ -1074,6 +1116,68 @@ int ccgpu_gf_decode_erasures(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8
     CU(cudaMemcpyAsync(failed + w0, d_fail, nw, cudaMemcpyDeviceToHost, st));
   }
   for (int s = 0; s < kSlots; ++s) CU(cudaStreamSynchronize(ctx->slot_stream[s]));
+  return CCGPU_OK;
+}
+
+int ccgpu_gf_decode_erasures_pgz(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8_t *words, uint64_t count,
+                                 const uint8_t *erasure_pos, const uint8_t *erasure_cnt, uint32_t max_erasures,
+                                 uint8_t *corrected, uint8_t *n_errors, uint8_t *failed) {
+  if (!ctx || !code || !words || !corrected || !failed || !erasure_pos || !erasure_cnt)
+    return fail(ctx, CCGPU_ERR_INVALID, "null argument");
+  if (code->ctx != ctx) return fail(ctx, CCGPU_ERR_INVALID, "code was not created on this context");
+  if (code->spec.family != 0) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "the zero/one fill rule is for binary BCH codes");
+  if (max_erasures == 0 || max_erasures > 255) return fail(ctx, CCGPU_ERR_INVALID, "max_erasures must be in 1..255");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (count == 0) return CCGPU_OK;
+  CU(cudaSetDevice(ctx->device));
+  const size_t n = code->spec.n, me = max_erasures;
+  const bool dev = is_device_ptr(words);
+  if (dev && (!is_device_ptr(corrected) || !is_device_ptr(failed) || (n_errors && !is_device_ptr(n_errors)) ||
+              !is_device_ptr(erasure_pos) || !is_device_ptr(erasure_cnt)))
+    return fail(ctx, CCGPU_ERR_INVALID, "words is a device pointer: every other buffer must be one too");
+  const size_t per_word = 4 * n + 4 + (dev ? 0 : 2 * n + 3 + me);
+  const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(count, (size_t(256) << 20) / per_word));
+  const size_t work = 2 * align256(2 * chunk * n) + 2 * align256(2 * chunk);
+  const size_t staging = dev ? 0 : 2 * align256(chunk * n) + 3 * align256(chunk) + align256(chunk * me);
+  int rc = ensure_stage(ctx, work + staging + 256);
+  if (rc) return rc;
+  uint8_t *d_fill = static_cast<uint8_t *>(ctx->d_stage);  // both fills of every word, then the decoder's outputs for them
+  uint8_t *d_cand = d_fill + align256(2 * chunk * n);
+  uint8_t *d_cne = d_cand + align256(2 * chunk * n);
+  uint8_t *d_cfail = d_cne + align256(2 * chunk);
+  uint8_t *s_in = d_cfail + align256(2 * chunk);  // staging for host buffers
+  uint8_t *s_out = s_in + align256(chunk * n);
+  uint8_t *s_ne = s_out + align256(chunk * n);
+  uint8_t *s_fail = s_ne + align256(chunk);
+  uint8_t *s_ec = s_fail + align256(chunk);
+  uint8_t *s_ep = s_ec + align256(chunk);
+  for (uint64_t w0 = 0; w0 < count; w0 += chunk) {
+    const uint64_t nw = std::min(chunk, count - w0);
+    const uint8_t *in = words + w0 * n, *ep = erasure_pos + w0 * me, *ec = erasure_cnt + w0;
+    uint8_t *out = corrected + w0 * n, *ne = n_errors ? n_errors + w0 : nullptr, *fl = failed + w0;
+    if (!dev) {
+      CU(cudaMemcpyAsync(s_in, in, nw * n, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(s_ep, ep, nw * me, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(s_ec, ec, nw, cudaMemcpyHostToDevice, ctx->stream));
+      in = s_in, ep = s_ep, ec = s_ec, out = s_out, ne = s_ne, fl = s_fail;
+    }
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((nw * n + 255) / 256, uint64_t(ctx->sm_count) * 16));
+    pgz_fill_kernel<<<grid, 256, 0, ctx->stream>>>(in, ep, ec, static_cast<uint32_t>(me), static_cast<uint32_t>(n), nw, d_fill);
+    CU(cudaGetLastError());
+    const int grc = gf_launch(code->gf, d_fill, 2 * nw, nullptr, nullptr, 0, d_cand, d_cne, d_cfail, ctx->sm_count, ctx->stream);
+    if (grc == -3) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "code not supported by the algebraic kernel (t <= 31, 2t <= 64, step = 1)");
+    if (grc != 0) return cuda_fail(ctx, cudaGetLastError(), "gf_launch");
+    pgz_select_kernel<<<grid, 256, 0, ctx->stream>>>(in, d_cand, d_cne, d_cfail, ec, code->spec.t, static_cast<uint32_t>(n), nw, out,
+                                                     ne, fl);
+    CU(cudaGetLastError());
+    ctx->launches += 3;
+    if (!dev) {
+      CU(cudaMemcpyAsync(corrected + w0 * n, s_out, nw * n, cudaMemcpyDeviceToHost, ctx->stream));
+      if (n_errors) CU(cudaMemcpyAsync(n_errors + w0, s_ne, nw, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaMemcpyAsync(failed + w0, s_fail, nw, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+  }
   return CCGPU_OK;
 }
 

@@ -286,9 +286,11 @@ class Code:
     def set_recheck(self, enable):
         _check(self.ctx, _lib.lib().ccgpu_code_set_recheck(self._h, int(bool(enable))))
 
-    def gf_decode(self, words, out=None, erasures=None):
+    def gf_decode(self, words, out=None, erasures=None, pgz_fill=False):
         """cyclic::correct_(.., hard_decision_tag) per word -> corrected, n_errors, failed.
-        erasures: optional (positions[count, max_e] uint8, counts[count] uint8)"""
+        erasures: optional (positions[count, max_e] uint8, counts[count] uint8); pgz_fill=True handles them like the
+        reference's PGZ decoder of binary BCH codes (zero fill / one fill, bch.h:97-149) instead of the
+        errors-and-erasures locator"""
         if _is_torch(words):
             import torch
             words = words.contiguous().view(-1, self.n)
@@ -310,9 +312,9 @@ class Code:
             if not _is_torch(epos):
                 epos = np.ascontiguousarray(epos, np.uint8).reshape(cnt, -1)
                 ecnt = np.ascontiguousarray(ecnt, np.uint8)
-            self.ctx._check(_lib.lib().ccgpu_gf_decode_erasures(self.ctx._h, self._h, _ptr(words), cnt, _ptr(epos),
-                                                                _ptr(ecnt), epos.shape[1], _ptr(corrected), _ptr(nerr),
-                                                                _ptr(failed)))
+            fn = _lib.lib().ccgpu_gf_decode_erasures_pgz if pgz_fill else _lib.lib().ccgpu_gf_decode_erasures
+            self.ctx._check(fn(self.ctx._h, self._h, _ptr(words), cnt, _ptr(epos), _ptr(ecnt), epos.shape[1],
+                               _ptr(corrected), _ptr(nerr), _ptr(failed)))
         return corrected, nerr, failed
 
 

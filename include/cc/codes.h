@@ -293,9 +293,19 @@ private:
   }
   template <typename In>
   void correct_erased(const In &b, const std::vector<unsigned> &er, uint8_t *out, uint8_t *failed, std::false_type) const {
-    if (er.size() > 30) throw decoding_failure("Number of erasures exceed what the engine supports (30).");
     std::vector<uint8_t> w, pos(30, 0);
     for (const auto &e : b) w.push_back(std::is_signed<typename In::value_type>::value ? (e < 0 ? 1 : 0) : static_cast<uint8_t>(e));
+    if (std::is_same<Algorithm, peterson_gorenstein_zierler_tag>::value && h_->info.family == 0) {
+      // binary BCH + PGZ: the reference fills the erasures with zeros, then ones, and keeps the better decode (bch.h:97-149)
+      if (er.size() > 255) throw decoding_failure("Number of erasures exceed error correction capability.");
+      pos.assign(er.size(), 0);
+      for (size_t i = 0; i < er.size(); ++i) pos[i] = static_cast<uint8_t>(er[i]);
+      const uint8_t cnt = static_cast<uint8_t>(er.size());
+      h_->ctx->check(ccgpu_gf_decode_erasures_pgz(h_->ctx->get(), h_->code, w.data(), 1, pos.data(), &cnt,
+                                                  static_cast<uint32_t>(er.size()), out, nullptr, failed));
+      return;
+    }
+    if (er.size() > 30) throw decoding_failure("Number of erasures exceed what the engine supports (30).");
     for (size_t i = 0; i < er.size(); ++i) pos[i] = static_cast<uint8_t>(er[i]);
     const uint8_t cnt = static_cast<uint8_t>(er.size());
     h_->ctx->check(ccgpu_gf_decode_erasures(h_->ctx->get(), h_->code, w.data(), 1, pos.data(), &cnt, 30, out, nullptr, failed));

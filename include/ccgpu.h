@@ -246,6 +246,16 @@ int ccgpu_gf_decode(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8_t *words
 int ccgpu_gf_decode_erasures(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8_t *words, uint64_t count,
                              const uint8_t *erasure_pos, const uint8_t *erasure_cnt, uint32_t max_erasures,
                              uint8_t *corrected, uint8_t *n_errors, uint8_t *failed);
+
+/* binary BCH with erasures as the reference's PGZ decoder handles them (primitive_bch::correct(b, erasures,
+ * peterson_gorenstein_zierler_tag), codes/bch.h:97-149): the erased positions are filled with zeros, then with
+ * ones, both words are decoded errors-only (cyclic.h:207-252), and the success that corrected fewer positions is
+ * returned (ties: the zero fill); failed = 1 when both fail or when a word has more than 2t erasures (:104-106).
+ * erasure_cnt[w] = 0 is plain decoding.  n_errors is the count of the returned candidate (errors in the filled
+ * word).  max_erasures <= 255; buffers as in ccgpu_gf_decode_erasures. */
+int ccgpu_gf_decode_erasures_pgz(ccgpu_ctx *ctx, const ccgpu_code *code, const uint8_t *words, uint64_t count,
+                                 const uint8_t *erasure_pos, const uint8_t *erasure_cnt, uint32_t max_erasures,
+                                 uint8_t *corrected, uint8_t *n_errors, uint8_t *failed);
 /* 1: always recompute the syndromes of the corrected word (cyclic.h:243-248).  Off by default: for
  * erasure-free words the check is implied by "deg Lambda <= t and deg Lambda distinct roots" (DESIGN.md 4). */
 int ccgpu_code_set_recheck(ccgpu_code *code, int enable);

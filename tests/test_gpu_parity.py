@@ -578,3 +578,31 @@ def test_mbbp_point(ctx, catalogue):
     one = code.awgn_point(eb, frames, "NMS", 0.8, seed=5, point=2, frame0=64)
     assert c["frame_errors"] < 0.8 * one["frame_errors"], (c, one)
     assert c["iterations"] > one["iterations"]
+
+
+def test_pgz_erasure_rule(ctx, catalogue):
+    """ccgpu_gf_decode_erasures_pgz == the reference's primitive_bch<.., pgz_tag>::correct(b, erasures) (bch.h:97-149)
+    on the vectors the reference produced (oracle/make_golden_pgz.py); host and device pointers"""
+    import torch
+    g = load_golden("hard_pgz_erasures.npz")
+    for name in ("bch_15_7", "bch_31_16", "bch_63_36", "bch_63_45"):
+        code = make_code(ctx, catalogue[name])
+        rec, epos, ecnt = g[name + ".received"], g[name + ".epos"], g[name + ".ecnt"]
+        out, nerr, failed = code.gf_decode(rec, erasures=(epos, ecnt), pgz_fill=True)
+        clean = g[name + ".solver_defect"] == 0   # the reference's PGZ solver malfunctions on a few t = 5 words
+        assert np.array_equal(failed[clean], (g[name + ".status"][clean] != 0).astype(np.uint8)), name
+        ok = clean & (failed == 0)
+        assert np.array_equal(out[ok], g[name + ".corrected"][ok]), name
+        assert np.array_equal(out[failed != 0], rec[failed != 0])  # a failed word comes back as received
+        # where the solver defect strikes, the engine still returns a codeword within the radius
+        bad = ~clean
+        assert (failed[bad] == 0).all() and np.array_equal(out[bad], g[name + ".words"][bad])
+        dev = code.gf_decode(torch.from_numpy(rec).cuda(), erasures=(torch.from_numpy(epos).cuda(), torch.from_numpy(ecnt).cuda()),
+                             pgz_fill=True)
+        ctx.sync()
+        assert np.array_equal(dev[0].cpu().numpy(), out) and np.array_equal(dev[2].cpu().numpy(), failed)
+        assert np.array_equal(dev[1].cpu().numpy(), nerr)
+        # no erasures: the plain decoder
+        plain = code.gf_decode(rec)
+        none = code.gf_decode(rec, erasures=(epos, np.zeros_like(ecnt)), pgz_fill=True)
+        assert all(np.array_equal(a, b) for a, b in zip(plain, none))
