@@ -144,6 +144,29 @@ def cpu_reference(ebno, seconds, frames_per_thread=0):
     return frames / el, cores, "port", sum(r[1] for r in res), frames
 
 
+def cpu_reference_point(q, errors, variant_id, ebno, seconds, threads=None):
+    """cpu_baseline leg for the other configurations (tools/bench_extra.py calls this instead of touching oracle/
+    itself): the reference's soft decoder `variant_id` (0 MS, 1 NMS, ...) of BCH(2^q - 1, t = errors) on the host
+    cores -> (frames, word_errors, seconds) or None when the reference library is not built"""
+    import ccref
+    if not ccref.available():
+        return None
+    ref = ccref.Ref()
+    return ref.awgn_baseline(ccref.FAM_BCH, q, ccref.CAP_ERRORS, errors, ccref.ALG_SOFT0 + variant_id, ebno, seed=0,
+                             seconds=seconds, threads=threads or (os.cpu_count() or 1))
+
+
+def cpu_reference_rs(q, errors, words):
+    """cpu_baseline leg: the reference's Euklid decoder of RS(2^q - 1, t = errors) on one core -> words/s or None"""
+    import ccref
+    if not ccref.available():
+        return None
+    ref = ccref.Ref()
+    t0 = time.perf_counter()
+    ref.hard_correct(ccref.FAM_RS, q, ccref.CAP_ERRORS, errors, ccref.ALG_EUKLID, words)
+    return len(words) / (time.perf_counter() - t0)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:

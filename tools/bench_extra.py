@@ -14,7 +14,6 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 
 def main():
@@ -28,11 +27,7 @@ def main():
     import channelcoding_b200 as cc
     ctx = cc.Context(0)
     ctx.use_torch_stream()
-    ref = None
-    if not args.no_cpu:
-        import ccref
-        if ccref.available():
-            ref = ccref.Ref()
+    import bench  # the CPU legs go through bench.py's cpu_baseline helpers (the only code outside tests/ that may run oracle/)
     cores = os.cpu_count()
 
     def fused(name, code, ebno, frames, variant, alpha=1.0, beta=0.0, stop=0, refkey=None, label=""):
@@ -51,26 +46,26 @@ def main():
                 "frames_per_s": frames / (ms * 1e-3), "info_bits_per_s": frames / (ms * 1e-3) * code.l, "ms": ms,
                 "wer": float(c[1]) / frames, "ber": float(c[2]) / frames / code.n, "avg_iterations": float(c[3]) / frames,
                 "kernel": {1: "ms_cyclic", 2: "ms_csr"}[code.kernel]}
-        if ref is not None and refkey is not None:
-            f, w, el = ref.awgn_baseline(*refkey, ebno, seed=0, seconds=args.cpu_seconds, threads=cores)
+        cpu = None if (args.no_cpu or refkey is None) else bench.cpu_reference_point(*refkey, ebno, args.cpu_seconds, cores)
+        if cpu is not None:
+            f, w, el = cpu
             line["cpu_reference"] = {"frames_per_s": f / el, "cores": cores, "wer": w / f, "frames": f}
             line["speedup_vs_cpu"] = line["frames_per_s"] / (f / el)
         print(json.dumps(line), flush=True)
 
     scale = 0.1 if args.quick else 1.0
-    from ccref import ALG_SOFT0, CAP_ERRORS, FAM_BCH
     c15 = ctx.bch(4, errors=2)
     for eb in (1.0, 3.0, 6.0):
-        fused("BCH(15,7) MS", c15, eb, int(2e7 * scale), "MS", refkey=(FAM_BCH, 4, CAP_ERRORS, 2, ALG_SOFT0 + 0))
+        fused("BCH(15,7) MS", c15, eb, int(2e7 * scale), "MS", refkey=(4, 2, 0))
     c63 = ctx.bch(6, errors=5)
     for eb in (2.0, 4.0, 6.0):
-        fused("BCH(63,36) NMS", c63, eb, int(2e7 * scale), "NMS", 0.8, refkey=(FAM_BCH, 6, CAP_ERRORS, 5, ALG_SOFT0 + 1))
+        fused("BCH(63,36) NMS", c63, eb, int(2e7 * scale), "NMS", 0.8, refkey=(6, 5, 1))
     fused("BCH(63,36) NMS gf2-stop", c63, 4.0, int(2e7 * scale), "NMS", 0.8, stop=1)
     for v, a, b in (("MS", 1, 0), ("OMS", 1, 0.01), ("SCMS1", 1, 0), ("SCMS2", 1, 0), ("2DNMS", 0.9, 0.9)):
         fused("BCH(63,36) " + v, c63, 4.0, int(1e7 * scale), v, a, b)
     c127 = ctx.bch(7, errors=10)
     for eb in (3.0, 5.0):
-        fused("BCH(127,64) NMS", c127, eb, int(4e6 * scale), "NMS", 0.8, refkey=(FAM_BCH, 7, CAP_ERRORS, 10, ALG_SOFT0 + 1))
+        fused("BCH(127,64) NMS", c127, eb, int(4e6 * scale), "NMS", 0.8, refkey=(7, 10, 1))
     c127.set_rows(127)
     fused("BCH(127,64) NMS redundant H (127 rows)", c127, 4.0, int(2e6 * scale), "NMS", 0.8, stop=1, label=", redundant")
     c127.set_rows(63)
@@ -96,7 +91,7 @@ def main():
                               "undetected": c["undetected"], "avg_iterations_all_bases": c["iterations"] / frames}), flush=True)
     c255 = ctx.bch(8, errors=18)
     for eb in (4.0, 6.0):
-        fused("BCH(255,131) NMS", c255, eb, int(2e5 * scale), "NMS", 0.8, refkey=(FAM_BCH, 8, CAP_ERRORS, 18, ALG_SOFT0 + 1))
+        fused("BCH(255,131) NMS", c255, eb, int(2e5 * scale), "NMS", 0.8, refkey=(8, 18, 1))
 
     # ---- RS(255,223): 1e7 codewords, error count uniform 0..16 plus a beyond-t slice
     rs = ctx.rs(8, 16)
@@ -132,12 +127,9 @@ def main():
     t0 = time.perf_counter()
     rs.gf_decode(h_words, out=h_out)
     line["e2e_codewords_per_s"] = len(h_words) / (time.perf_counter() - t0)
-    if ref is not None:
-        from ccref import ALG_EUKLID, FAM_RS
-        t0 = time.perf_counter()
-        ref.hard_correct(FAM_RS, 8, CAP_ERRORS, 16, ALG_EUKLID, bad[:2048])
-        el = time.perf_counter() - t0
-        line["cpu_reference"] = {"codewords_per_s_one_core": 2048 / el, "cores_used": 1,
+    rate = None if args.no_cpu else bench.cpu_reference_rs(8, 16, bad[:2048])
+    if rate is not None:
+        line["cpu_reference"] = {"codewords_per_s_one_core": rate, "cores_used": 1,
                                  "note": "euklid_tag, stdout of rs.h:53-75 silenced"}
     print(json.dumps(line), flush=True)
     ctx.close()
