@@ -86,6 +86,7 @@ def lib():
     L.ccgpu_awgn_point.argtypes = [vp, vp, C.POINTER(MsParams), dbl, u64, u32, u64, u64, vp]
     L.ccgpu_awgn_point_hard.argtypes = [vp, vp, dbl, u64, u32, u64, u64, vp]
     L.ccgpu_bitflip_point.argtypes = [vp, vp, C.POINTER(MsParams), u32, u64, u64, vp]
+    L.ccgpu_awgn_point_uncoded.argtypes = [vp, u32, dbl, dbl, u64, u32, u64, u64, vp]
     L.ccgpu_decode_llr_mbbp.argtypes = [vp, vp, C.POINTER(MsParams), vp, u32, vp, u64, vp, vp, vp, vp, vp]
     L.ccgpu_awgn_point_mbbp.argtypes = [vp, vp, C.POINTER(MsParams), vp, u32, dbl, u64, u32, u64, u64, vp]
     L.ccgpu_gf_decode.argtypes = [vp, vp, vp, u64, vp, vp, vp]
@@ -104,5 +105,5 @@ EXPORTS = ["ccgpu_abi_version", "ccgpu_create", "ccgpu_destroy", "ccgpu_last_err
            "ccgpu_code_from_dense", "ccgpu_code_set_rows", "ccgpu_code_destroy", "ccgpu_code_get_info",
            "ccgpu_code_to_string", "ccgpu_code_H", "ccgpu_code_H_alt", "ccgpu_code_poly", "ccgpu_gf_tables", "ccgpu_encode",
            "ccgpu_decode_llr", "ccgpu_sigma", "ccgpu_shannon_limit_db", "ccgpu_sweep_start_ebno", "ccgpu_sweep_samples", "ccgpu_awgn_llr", "ccgpu_awgn_point", "ccgpu_awgn_point_hard", "ccgpu_bitflip_point",
-           "ccgpu_gf_decode", "ccgpu_gf_decode_erasures", "ccgpu_code_set_recheck", "ccgpu_decode_llr_mbbp", "ccgpu_gf_decode_erasures_pgz",
+           "ccgpu_gf_decode", "ccgpu_gf_decode_erasures", "ccgpu_code_set_recheck", "ccgpu_decode_llr_mbbp", "ccgpu_awgn_point_uncoded", "ccgpu_gf_decode_erasures_pgz",
            "ccgpu_awgn_point_mbbp"]

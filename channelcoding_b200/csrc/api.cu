@@ -312,6 +312,34 @@ __global__ void __launch_bounds__(256) pgz_select_kernel(const uint8_t *__restri
   }
 }
 
+// the "uncoded" decoder of the reference (codes/uncoded.h:36-46: hard decision, nothing else) inside one Eb/N0
+// point: one warp per frame, lane <-> Philox block, negative channel values counted on the fly
+__global__ void __launch_bounds__(256) awgn_uncoded_kernel(uint32_t n, float sigma, PhiloxKeys keys, uint32_t point,
+                                                           uint64_t frame0, uint64_t frames, unsigned long long *counters) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t nblk = (n + 3) >> 2;
+  const uint64_t warps = static_cast<uint64_t>(gridDim.x) * (blockDim.x >> 5);
+  unsigned long long c_frames = 0, c_ferr = 0, c_berr = 0;
+  for (uint64_t f = blockIdx.x * static_cast<uint64_t>(blockDim.x >> 5) + (threadIdx.x >> 5); f < frames; f += warps) {
+    unsigned neg = 0;
+    for (uint32_t blk = lane; blk < nblk; blk += 32) {
+      const float4 v = awgn_block(keys, point, frame0 + f, blk, sigma);
+      const float vv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+      for (int e = 0; e < 4; ++e) neg += (4 * blk + e < n && vv[e] < 0.0f) ? 1u : 0u;
+    }
+    for (int o = 16; o > 0; o >>= 1) neg += __shfl_xor_sync(0xffffffffu, neg, o);
+    c_frames += 1;
+    c_berr += neg;
+    c_ferr += neg ? 1 : 0;
+  }
+  if (lane == 0) {
+    if (c_frames) atomicAdd(counters + C_FRAMES, c_frames);
+    if (c_ferr) atomicAdd(counters + C_FRAME_ERR, c_ferr);
+    if (c_berr) atomicAdd(counters + C_BIT_ERR, c_berr);
+  }
+}
+
 bool columns_covered(const CodeSpec &s) {
   for (unsigned c = 0; c < s.n; ++c) {
     bool any = false;
@@ -1025,6 +1053,30 @@ int ccgpu_awgn_point_mbbp(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms
     if (rc) return rc;
     rc = mbbp_run(ctx, code, params, shifts, n_bases, s_y, nf, base + io, s_bits, nullptr, s_iter, s_failed, s_chosen, counters);
     if (rc) return rc;
+  }
+  if (!dev) {
+    CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(ccgpu_counters), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out = *ctx->h_counters;
+  }
+  return CCGPU_OK;
+}
+
+int ccgpu_awgn_point_uncoded(ccgpu_ctx *ctx, uint32_t n, double rate, double ebno_db, uint64_t seed, uint32_t point,
+                             uint64_t frame0, uint64_t frames, ccgpu_counters *out) {
+  if (!ctx || !out || n == 0) return fail(ctx, CCGPU_ERR_INVALID, "null argument");
+  if (!(rate > 0.0)) return fail(ctx, CCGPU_ERR_INVALID, "rate must be positive");
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CU(cudaSetDevice(ctx->device));
+  const bool dev = is_device_ptr(out);
+  unsigned long long *counters = dev ? reinterpret_cast<unsigned long long *>(out) : ctx->d_counters;
+  if (!dev) CU(cudaMemsetAsync(ctx->d_counters, 0, sizeof(ccgpu_counters), ctx->stream));
+  if (frames) {
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>((frames + 7) / 8, uint64_t(ctx->sm_count) * 8));
+    awgn_uncoded_kernel<<<grid, 256, 0, ctx->stream>>>(n, static_cast<float>(ccgpu_sigma(rate, ebno_db)), philox_round_keys(seed),
+                                                       point, frame0, frames, counters);
+    CU(cudaGetLastError());
+    ctx->launches++;
   }
   if (!dev) {
     CU(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(ccgpu_counters), cudaMemcpyDeviceToHost, ctx->stream));

@@ -125,6 +125,13 @@ class Context:
         return Code(self, h)
 
     # ---- channel
+    def awgn_point_uncoded(self, n, ebno_db, frames, rate=0.5, seed=0, point=0, frame0=0):
+        """one Eb/N0 point over the reference's `uncoded` pseudo-decoder (codes/uncoded.h) -> counters"""
+        c = Counters()
+        self._check(_lib.lib().ccgpu_awgn_point_uncoded(self._h, n, float(rate), float(ebno_db), seed, point, frame0, frames,
+                                                        C.addressof(c)))
+        return c.as_dict()
+
     def awgn_llr(self, n, sigma, seed, point, frame0, frames, out=None):
         if out is None:
             out = np.empty((frames, n), np.float32)

@@ -362,4 +362,30 @@ public:
   explicit rs(int device = 0) : cyclic_base<Sigma>(make(device)) {}
 };
 
+// codes/uncoded.h:10-47 -- the pseudo-decoder of simulation/uncoded.c++: n symbols, hard decision, nominal rate 0.5.
+// `correct` is the decision itself (there is no arithmetic to offload); the Monte-Carlo point runs on the device.
+class uncoded {
+  std::shared_ptr<context> ctx_;
+
+public:
+  static constexpr double rate = 0.5;
+  const unsigned n;
+  explicit uncoded(const unsigned l, int device = 0) : ctx_(context::shared(device)), n(l) {}
+  std::string to_string() const { return std::to_string(n) + "-uncoded"; }
+  template <typename Return_type = uint8_t, typename InputSequence>
+  std::vector<Return_type> correct(const InputSequence &b) const {
+    std::vector<Return_type> r;
+    r.reserve(n);
+    for (const auto &e : b)
+      r.push_back(Return_type(std::is_signed<typename InputSequence::value_type>::value ? (e < 0) : static_cast<bool>(e)));
+    r.resize(n, Return_type(0));
+    return r;
+  }
+  ccgpu_counters awgn_point(double ebno_db, uint64_t frames, uint64_t seed, uint32_t point, uint64_t frame0 = 0) const {
+    ccgpu_counters c{};
+    ctx_->check(ccgpu_awgn_point_uncoded(ctx_->get(), n, rate, ebno_db, seed, point, frame0, frames, &c));
+    return c;
+  }
+};
+
 }  // namespace cc

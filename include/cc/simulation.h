@@ -111,10 +111,36 @@ class decoder {
     }
   };
 
+  // codes/uncoded.h plugged into the simulations (simulation/uncoded.c++:54)
+  class uncoded_model : public decoder_concept {
+    uncoded implementation;
+
+  public:
+    explicit uncoded_model(uncoded arg) : implementation(std::move(arg)) {}
+    std::vector<uint8_t> correct(const std::vector<float> &b) const override { return implementation.correct<uint8_t>(b); }
+    std::string to_string() const override { return implementation.to_string(); }
+    double rate() const override { return uncoded::rate; }
+    unsigned n() const override { return implementation.n; }
+    bool soft() const override { return false; }
+    ccgpu_counters awgn_point(double e, uint64_t f, uint64_t s, uint32_t p, uint64_t f0) const override {
+      return implementation.awgn_point(e, f, s, p, f0);
+    }
+    ccgpu_counters bitflip_point(unsigned weight) const override {  // every flipped pattern is a word error
+      ccgpu_counters c{};
+      double patterns = 1.0;
+      for (unsigned i = 1; i <= weight; ++i) patterns = patterns * (implementation.n - weight + i) / i;
+      c.frames = static_cast<uint64_t>(patterns + 0.5);
+      c.frame_errors = weight ? c.frames : 0;
+      c.bit_errors = c.frames * weight;
+      return c;
+    }
+  };
+
   std::shared_ptr<const decoder_concept> _self;
 
 public:
   template <typename T> decoder(T d) : _self(std::make_shared<decoder_model<T> >(std::move(d))) {}
+  decoder(uncoded d) : _self(std::make_shared<uncoded_model>(std::move(d))) {}
   template <typename InputSequence> std::vector<uint8_t> correct(const InputSequence &b) const {
     return _self->correct(std::vector<float>(b.begin(), b.end()));
   }

@@ -213,6 +213,13 @@ int ccgpu_awgn_point_mbbp(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms
                           uint32_t n_bases, double ebno_db, uint64_t seed, uint32_t point, uint64_t frame0, uint64_t frames,
                           ccgpu_counters *out);
 
+/* one Eb/N0 point of awgn_simulation over the reference's `uncoded` pseudo-decoder (codes/uncoded.h:10-47: n symbols,
+ * hard decision only, nominal rate 0.5 as in simulation/uncoded.c++:54): channel + decision + error test on the
+ * device.  Same noise stream as ccgpu_awgn_point for the same (seed, point, frame).  Only frames, frame_errors and
+ * bit_errors are counted. */
+int ccgpu_awgn_point_uncoded(ccgpu_ctx *ctx, uint32_t n, double rate, double ebno_db, uint64_t seed, uint32_t point,
+                             uint64_t frame0, uint64_t frames, ccgpu_counters *out);
+
 /* the same Eb/N0 point for the HARD-decision tags (BM / PGZ / Euklid decoders of benchmark.c++:29-64 inside
  * awgn_simulation): channel, hard decision (codes/codes.h:43-52: bit = y < 0), algebraic decode
  * (cyclic.h:207-252) and the error test, all on the device; binary BCH codes.  iterations stays 0. */

@@ -83,3 +83,30 @@ def test_python_sweep_equals_cli_sweep(bins, tmp_path):
         assert open(py_dir / (name + ".log")).read() == open(cli_dir / (name + ".log")).read(), tag
         assert res[0]["ebno"] == 1.0 and res[0]["frames"] == 10000 and res[-1]["wer"] < res[0]["wer"]
     ctx.close()
+
+
+def test_uncoded_cli_without_gpu_is_loud(bins, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([bins["uncoded"], "--l", "63", "--out", str(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and "no usable CUDA device" in (r.stdout + r.stderr)
+
+
+@pytest.mark.gpu
+def test_uncoded_program(bins, tmp_path):
+    """simulation/uncoded.c++ on the GPU: "<l>-uncoded.log" with the sweep schedule of rate 0.5 and the word error
+    rate of l uncoded BPSK symbols, 1 - (1 - Q(1/sigma))^l"""
+    import math
+    r = subprocess.run([bins["uncoded"], "--l", "63", "--seed", "5", "--max-samples", "400000", "--out", str(tmp_path)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = open(tmp_path / "63-uncoded.log").read().splitlines()
+    assert lines[0] == "   ebno                   wer"
+    pts = [tuple(map(float, x.split())) for x in lines[1:]]
+    assert pts[0][0] == 1.0 and len(pts) >= 10   # one step above the rounded-down limit of rate 0.5 (0.188 dB)
+    for eb, wer in pts:
+        sigma = 1.0 / math.sqrt(2 * 0.5 * 10 ** (eb / 10))
+        q = 0.5 * math.erfc(1.0 / (sigma * math.sqrt(2)))
+        expect = 1 - (1 - q) ** 63
+        assert abs(wer - expect) < 5 * math.sqrt(expect * (1 - expect) / 1e4) + 1e-4, (eb, wer, expect)

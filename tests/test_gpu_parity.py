@@ -606,3 +606,14 @@ def test_pgz_erasure_rule(ctx, catalogue):
         plain = code.gf_decode(rec)
         none = code.gf_decode(rec, erasures=(epos, np.zeros_like(ecnt)), pgz_fill=True)
         assert all(np.array_equal(a, b) for a, b in zip(plain, none))
+
+
+def test_uncoded_point(ctx):
+    """ccgpu_awgn_point_uncoded == hard decisions on the channel kernel's output for the same (seed, point, frames)"""
+    import channelcoding_b200 as cc
+    for n, eb in ((63, 3.0), (15, 6.0), (200, 5.0)):
+        frames = 50000
+        c = ctx.awgn_point_uncoded(n, eb, frames, seed=3, point=9, frame0=17)
+        y = ctx.awgn_llr(n, np.float32(cc.sigma(0.5, eb)), seed=3, point=9, frame0=17, frames=frames)
+        neg = y < 0
+        assert c["frames"] == frames and c["bit_errors"] == int(neg.sum()) and c["frame_errors"] == int(neg.any(axis=1).sum())
