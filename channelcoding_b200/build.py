@@ -88,6 +88,7 @@ def build_tools(force=False):
             os.path.join(root, "include", "cc", "simulation.h")]
     jobs = [(os.path.join(TOOLS_BIN, "benchmark"), os.path.join(root, "tools", "benchmark.cc")),
             (os.path.join(TOOLS_BIN, "uncoded"), os.path.join(root, "tools", "uncoded.cc")),
+            (os.path.join(TOOLS_BIN, "bitflips"), os.path.join(root, "tools", "bitflips.cc")),
             (os.path.join(TOOLS_BIN, "host_layer_test"), os.path.join(root, "tests", "cpp", "host_layer_test.cc"))]
 
     def one(job):
@@ -101,7 +102,7 @@ def build_tools(force=False):
         if r.returncode != 0:
             raise RuntimeError("g++ failed for %s:\n%s" % (src, r.stdout + r.stderr))
         return out
-    with concurrent.futures.ThreadPoolExecutor(max_workers=3) as ex:
+    with concurrent.futures.ThreadPoolExecutor(max_workers=4) as ex:
         return list(ex.map(one, jobs))
 
 

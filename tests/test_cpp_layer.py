@@ -110,3 +110,18 @@ def test_uncoded_program(bins, tmp_path):
         q = 0.5 * math.erfc(1.0 / (sigma * math.sqrt(2)))
         expect = 1 - (1 - q) ** 63
         assert abs(wer - expect) < 5 * math.sqrt(expect * (1 - expect) / 1e4) + 1e-4, (eb, wer, expect)
+
+
+@pytest.mark.gpu
+def test_bitflips_program(bins, tmp_path, kat):
+    """simulation/bitflips.c++ on the GPU: nine decoders of BCH(31,16,7), every pattern of 0..3 flipped bits, each log
+    equals the counts the reference produced (tests/golden/kat.json, Table 3 of the report)"""
+    r = subprocess.run([bins["bitflips"], "--errors", "3", "--out", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.splitlines()[:9] == ["(31, 16, 7)-" + t for t in ("BM", "PGZ", "EUKLID", "MS", "NMS", "OMS", "SCMS1", "SCMS2", "2DNMS")]
+    for tag in ("BM", "PGZ", "EUKLID", "MS", "NMS", "OMS", "SCMS1", "SCMS2", "2DNMS"):
+        lines = open(tmp_path / ("(31, 16, 7)-%s.log" % tag)).read().splitlines()
+        assert lines[0] == " errors                   wer" and len(lines) == 5
+        for w in range(4):
+            row = kat["bitflip_31_16_7"][str(w)]
+            assert abs(float(lines[1 + w].split()[1]) - row[tag] / row["patterns"]) < 1e-12, (tag, w)
