@@ -58,9 +58,7 @@ struct Gf {
 };
 
 __device__ __forceinline__ unsigned xor_reduce(unsigned v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v ^= __shfl_xor_sync(kAll, v, o);
-  return v;
+  return __reduce_xor_sync(kAll, v);  // REDUX.XOR: one instruction instead of a five-step shuffle butterfly
 }
 
 // syndromes of `word` (zero padded to a multiple of 4 bytes per segment) into synd[0..nroots)
