@@ -127,10 +127,13 @@ def main():
     nh = len(h_words)
     h_out = (torch.empty((nh, 255), dtype=torch.uint8).pin_memory().numpy(), torch.empty(nh, dtype=torch.uint8).pin_memory().numpy(),
              torch.empty(nh, dtype=torch.uint8).pin_memory().numpy())
-    rs.gf_decode(h_words[:100000], out=(h_out[0][:100000], h_out[1][:100000], h_out[2][:100000]))  # warm-up: staging slots
-    t0 = time.perf_counter()
-    rs.gf_decode(h_words, out=h_out)
-    line["e2e_codewords_per_s"] = nh / (time.perf_counter() - t0)
+    best = 1e9
+    for _ in range(3):  # the first call sizes the staging slots and touches the pinned pages
+        t0 = time.perf_counter()
+        rs.gf_decode(h_words, out=h_out)
+        best = min(best, time.perf_counter() - t0)
+    line["e2e_codewords_per_s"] = nh / best
+    line["e2e_GBps_each_way"] = nh * 255 / best / 1e9
     assert np.array_equal(h_out[2][:base], out[2][:base].cpu().numpy())
     rate = None if args.no_cpu else bench.cpu_reference_rs(8, 16, bad[:2048])
     if rate is not None:
