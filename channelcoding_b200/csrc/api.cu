@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -478,6 +479,15 @@ int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsP
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(want, c->grid_max[vn]));
     CU(cudaMemsetAsync(work, 0, sizeof(unsigned long long), stream));
     mp.work = work;
+    {  // guided self-scheduling of the frame queue: a warp takes up to 32 frame indices per atomic while more than
+       // 4 x 32 frames per warp are left, fewer towards the end (work_shift = log2(4 x warps))
+      const uint64_t warps = uint64_t(grid) * (e->threads / 32);
+      unsigned shift = 0;
+      while ((uint64_t(1) << shift) < 4 * warps) ++shift;
+      mp.work_batch = 32;
+      mp.work_shift = shift;
+      if (const char *env = std::getenv("CCGPU_WORK_BATCH")) mp.work_batch = std::max(1, std::atoi(env));
+    }
     void *args[] = { &mp };
     CU(cudaLaunchKernel(reinterpret_cast<const void *>(e->fn), dim3(grid), dim3(e->threads), args, c->smem[vn], stream));
     ctx->launches++;

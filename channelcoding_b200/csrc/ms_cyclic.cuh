@@ -118,6 +118,16 @@ __device__ __forceinline__ float2 cn_magnitude_pair(const MsParams &p, float m1,
   return make_float2(m1, m2);
 }
 
+// guided self-scheduling: how many frame indices to take from the queue now -- work_batch while plenty are left,
+// fewer towards the end so that no warp sits on a long private tail.  The queue head is not read (a load of the
+// line every warp hammers with atomics costs a second round trip): it is estimated from the end of the warp's own
+// previous batch plus what all warps took meanwhile (about warps x that batch; 4 x warps = 2^work_shift).
+__device__ __forceinline__ unsigned guided_batch(const MsParams &p, long long own_next, unsigned last_batch) {
+  const long long rem = static_cast<long long>(p.frames) - own_next - (static_cast<long long>(last_batch) << (p.work_shift - 2));
+  const long long g = rem > 0 ? (rem >> p.work_shift) : 0;
+  return g < 1 ? 1u : (g < static_cast<long long>(p.work_batch) ? static_cast<unsigned>(g) : p.work_batch);
+}
+
 __device__ __forceinline__ unsigned long long binom(unsigned n, unsigned r) {
   if (r > n) return 0ull;
   unsigned long long v = 1ull;
@@ -243,6 +253,17 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
   unsigned cnt_frames = 0, cnt_ferr = 0, cnt_berr = 0, cnt_iter = 0, cnt_fail = 0, cnt_und = 0;
 #endif
   constexpr int NBLK = (N + 3) >> 2;
+  static_assert(FPW <= 8, "grant slots");
+  __shared__ long long pool_next_s[kMsThreads / 32];  // frame indices already taken from the queue: next one ..
+  __shared__ int pool_left_s[kMsThreads / 32];        // .. and how many are left
+  __shared__ long long grant_s[kMsThreads / 32][FPW > 1 ? FPW : 1];
+  __shared__ unsigned pool_batch_s[kMsThreads / 32];   // size of the batch taken last
+  if (lane == 0) {
+    pool_left_s[warp_in_cta] = 0;
+    pool_batch_s[warp_in_cta] = 0;
+    pool_next_s[warp_in_cta] = units;  // the queue starts behind the statically assigned first frames
+  }
+  __syncwarp();
 
   while (true) {
     if (__ballot_sync(kFull, active) == 0u) break;
@@ -520,8 +541,42 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
           cnt_ferr += (failed || nbits != 0) ? 1 : 0;
           cnt_und += (!failed && nbits != 0) ? 1 : 0;
 #endif
-          next = units + static_cast<long long>(atomicAdd(p.work, 1ull));  // dynamic schedule
         }
+      }
+      // dynamic schedule: every finishing group gets the next frame index of the warp's pool, which is refilled from
+      // the global queue head with ONE atomic per work_batch frames (one atomic per frame on one address caps the
+      // queue at 1.5e9 frames/s, measured; the small codes decode several times faster than that)
+      if (FPW == 1) {
+        if (fin && lane == 0) {  // fin is warp uniform here: one group per warp
+          int left = pool_left_s[warp_in_cta];
+          next = pool_next_s[warp_in_cta];
+          if (left == 0) {
+            left = static_cast<int>(guided_batch(p, next, pool_batch_s[warp_in_cta]));
+            pool_batch_s[warp_in_cta] = static_cast<unsigned>(left);
+            next = units + static_cast<long long>(atomicAdd(p.work, static_cast<unsigned long long>(left)));
+          }
+          pool_next_s[warp_in_cta] = next + 1;
+          pool_left_s[warp_in_cta] = left - 1;
+        }
+      } else {
+        const unsigned leadm = __ballot_sync(kFull, fin && is_lead);
+        if (lane == 0) {
+          int left = pool_left_s[warp_in_cta], slot = 0;
+          long long nx = pool_next_s[warp_in_cta];
+          for (unsigned m = leadm; m; m &= m - 1u, ++slot) {
+            if (left == 0) {
+              left = static_cast<int>(guided_batch(p, nx, pool_batch_s[warp_in_cta]));
+              pool_batch_s[warp_in_cta] = static_cast<unsigned>(left);
+              nx = units + static_cast<long long>(atomicAdd(p.work, static_cast<unsigned long long>(left)));
+            }
+            grant_s[warp_in_cta][slot] = nx++;
+            --left;
+          }
+          pool_next_s[warp_in_cta] = nx;
+          pool_left_s[warp_in_cta] = left;
+        }
+        __syncwarp();
+        if (fin && is_lead) next = grant_s[warp_in_cta][__popc(leadm & ((1u << lane) - 1u))];
       }
       next = __shfl_sync(kFull, next, lead_lane);
       if (fin) {

@@ -36,6 +36,8 @@ struct MsParams {
   uint8_t *failed;     // frames
   unsigned long long *counters;  // kCounterSlots, accumulated with atomics
   unsigned long long *work;      // dynamic frame queue head, zeroed by the host before the launch
+  unsigned work_batch;            // most frame indices a warp takes from the queue per atomic (>= 1)
+  unsigned work_shift;            // guided schedule: a warp takes min(work_batch, remaining >> work_shift) frames
 };
 
 // counter slots (ccgpu_counters layout)
