@@ -970,6 +970,7 @@ int ccgpu_awgn_point(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_para
   // sum-product extension needs log-likelihood ratios 2 y / sigma^2
   mp.llr_scale = params->variant == CCGPU_SPA ? 2.0f / (mp.sigma * mp.sigma) : 1.0f;
   mp.seed = seed;
+  mp.keys = philox_round_keys(seed);
   mp.point = point;
   mp.frame0 = frame0;
   mp.frames = frames;

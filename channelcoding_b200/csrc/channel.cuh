@@ -11,6 +11,8 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "ms_params.h"
+
 namespace ccgpu {
 
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
@@ -25,22 +27,6 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
   return c;
 }
 
-// Philox with the ten round keys precomputed on the host (they depend on the seed only): the rounds take their
-// key from the constant bank as a LOP3 operand instead of two uniform-datapath adds per round
-struct PhiloxKeys {
-  uint32_t x[10], y[10];
-};
-inline PhiloxKeys philox_round_keys(uint64_t seed) {
-  PhiloxKeys k;
-  uint32_t kx = static_cast<uint32_t>(seed), ky = static_cast<uint32_t>(seed >> 32);
-  for (int r = 0; r < 10; ++r) {
-    k.x[r] = kx;
-    k.y[r] = ky;
-    kx += 0x9E3779B9u;
-    ky += 0xBB67AE85u;
-  }
-  return k;
-}
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKeys &k) {
 #pragma unroll
   for (int round = 0; round < 10; ++round) {

@@ -76,7 +76,7 @@ __global__ void ms_csr_kernel(const __grid_constant__ MsParams p, const CsrView 
       for (int c = tid; c < n; c += nt) ybuf[c] = __ldg(p.y + fr * n + c);
     } else if (p.src == SRC_PHILOX) {
       for (int b = tid; b < ((n + 3) >> 2); b += nt) {
-        const float4 v = awgn_block(p.seed, p.point, p.frame0 + fr, b, p.sigma);
+        const float4 v = awgn_block(p.keys, p.point, p.frame0 + fr, b, p.sigma);
         const float vv[4] = { v.x * p.llr_scale, v.y * p.llr_scale, v.z * p.llr_scale, v.w * p.llr_scale };
 #pragma unroll
         for (int e = 0; e < 4; ++e)

@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VN>()) ms_cyclic_
           const int src_lane = f * k;
           const long long fr = __shfl_sync(kFull, my_frame, src_lane);
           if (bv && ((initm >> src_lane) & 1u)) {
-            const float4 v = awgn_block(p.seed, p.point, p.frame0 + static_cast<uint64_t>(fr), blk, p.sigma);
+            const float4 v = awgn_block(p.keys, p.point, p.frame0 + static_cast<uint64_t>(fr), blk, p.sigma);
             const int c0 = f * N + 4 * blk;
             const float vv[4] = { v.x * p.llr_scale, v.y * p.llr_scale, v.z * p.llr_scale, v.w * p.llr_scale };
 #pragma unroll

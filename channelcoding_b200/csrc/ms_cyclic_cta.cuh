@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(S::THREADS, CCGPU_MS_CTA_MINBLK) ms_cyclic_cta
       for (int c = tid; c < N; c += THREADS) ybuf[c] = __ldg(p.y + frame * N + c);
     } else if (p.src == SRC_PHILOX) {
       for (int b = tid; b < NBLK; b += THREADS) {
-        const float4 v = awgn_block(p.seed, p.point, p.frame0 + static_cast<uint64_t>(frame), b, p.sigma);
+        const float4 v = awgn_block(p.keys, p.point, p.frame0 + static_cast<uint64_t>(frame), b, p.sigma);
         const float vv[4] = { v.x * p.llr_scale, v.y * p.llr_scale, v.z * p.llr_scale, v.w * p.llr_scale };
 #pragma unroll
         for (int e = 0; e < 4; ++e)

@@ -12,6 +12,22 @@ enum : int { V_MS = 0, V_NMS = 1, V_OMS = 2, V_SCMS1 = 3, V_SCMS2 = 4, V_NMS2D =
 enum : int { STOP_REF = 0, STOP_GF2 = 1, STOP_NONE = 2 };
 enum : int { SRC_HBM = 0, SRC_PHILOX = 1, SRC_BITFLIP = 2 };
 
+// Philox with the ten round keys precomputed on the host (they depend on the seed only): the rounds take their
+// key from the constant bank as a LOP3 operand instead of two uniform-datapath adds per round
+struct PhiloxKeys {
+  uint32_t x[10], y[10];
+};
+inline PhiloxKeys philox_round_keys(uint64_t seed) {
+  PhiloxKeys k;
+  uint32_t kx = static_cast<uint32_t>(seed), ky = static_cast<uint32_t>(seed >> 32);
+  for (int r = 0; r < 10; ++r) {
+    k.x[r] = kx;
+    k.y[r] = ky;
+    kx += 0x9E3779B9u;
+    ky += 0xBB67AE85u;
+  }
+  return k;
+}
 // One launch of a min-sum kernel (passed as a __grid_constant__ kernel parameter).
 struct MsParams {
   // ---- parity-check matrix: n columns, k rows (the cyclic kernels know the tap offsets at compile time)
@@ -27,6 +43,7 @@ struct MsParams {
   float llr_scale;     // SRC_PHILOX: y is multiplied by this (2 / sigma^2 for sum-product, else 1)
   uint32_t point;
   uint64_t seed, frame0;
+  PhiloxKeys keys;     // SRC_PHILOX: the round keys of `seed` (channel.cuh)
   uint64_t frames;     // frames of this launch
   uint32_t flip_weight;  // SRC_BITFLIP: patterns of this weight, frame index = lexicographic rank
   // ---- outputs (nullable)
