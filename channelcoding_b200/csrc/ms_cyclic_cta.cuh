@@ -19,13 +19,17 @@
 #include "ms_shape_cta.h"
 
 #ifndef CCGPU_MS_CTA_MINBLK
-#define CCGPU_MS_CTA_MINBLK 1  /* measured: 5 CTAs per SM (96 registers, 108 bytes spilled) is 7 % slower than 4 (128 registers) */
+#define CCGPU_MS_CTA_MINBLK 4  /* one row per thread, plain / 2-D flavour: 4 CTAs per SM = 128 registers, no spills; \
+   measured: 5 (96 registers, 108 bytes spilled) is 7 % slower, an unconstrained allocation (168 registers, 3 CTAs) 12 % slower */
 #endif
 
 namespace ccgpu {
 
+// the two-rows-per-thread (wrap-around) shapes and the self-correcting flavour need more than 128 registers
+template <class S, int VN> constexpr int ms_cta_min_blocks() { return (S::RPL == 1 && VN != VN_SC) ? CCGPU_MS_CTA_MINBLK : 1; }
+
 template <class S, int VN>
-__global__ void __launch_bounds__(S::THREADS, CCGPU_MS_CTA_MINBLK) ms_cyclic_cta_kernel(const __grid_constant__ MsParams p) {
+__global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyclic_cta_kernel(const __grid_constant__ MsParams p) {
   constexpr int N = S::N, W = S::W, RPL = S::RPL, NPW = S::NPW, THREADS = S::THREADS, CPASS = S::CPASS;
   constexpr bool WRAP = S::WRAP, SC = VN == VN_SC;
   constexpr int NPAD = NPW * 32;
