@@ -105,10 +105,19 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyc
         if (SC) qold[i][j] = 0.0f;
       }
     __syncthreads();
+    // all channel values positive: iteration 0 decides the all-zero word and stops (see quick_ok in ms_cyclic.cuh);
+    // nothing has to be executed for it unless the totals L are wanted
+    bool allpos = true;
+    for (int c = tid; c < N; c += THREADS) allpos &= ybuf[c] > 0.0f;
+    const bool quick = __syncthreads_and(allpos) && p.L == nullptr && p.stop_rule != STOP_NONE && p.max_iter >= 1;
+    if (quick) {  // block-uniform
+      if (tid < CPASS * S::WPF) bword[tid] = 0u;
+      __syncthreads();
+    }
 
     int it = 0;
-    bool stop = false;
-    for (;; ++it) {
+    bool stop = quick;
+    for (; !quick; ++it) {
       // ============ VN + CN
       float f1s[RPL], f2s[RPL], m1v[RPL];
 #pragma unroll

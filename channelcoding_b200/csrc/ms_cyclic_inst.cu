@@ -1,5 +1,5 @@
 // ms_cyclic_inst.cu -- compiled once per -DCCGPU_GROUP=g: instantiates ms_cyclic_kernel for the
-// shapes of CCGPU_MS_LIST_g (ms_shapes_generated.h), four message-update flavours each, and
+// shapes of CCGPU_MS_LIST_g (ms_shapes_generated.h), four message-update flavours each plus the three QUICK ones, and
 // exposes them to the registry in ms_registry.cu.
 #include "ms_cyclic.cuh"
 #include "ms_shapes_generated.h"
@@ -28,7 +28,9 @@ template <class S, int VN> MsCyclicEntry make_entry(const char *name) {
 }
 
 #define X(NAME) make_entry<shapes::NAME, VN_PLAIN>(#NAME), make_entry<shapes::NAME, VN_SC>(#NAME), \
-                make_entry<shapes::NAME, VN_2D>(#NAME), make_entry<shapes::NAME, VN_SPA>(#NAME),
+                make_entry<shapes::NAME, VN_2D>(#NAME), make_entry<shapes::NAME, VN_SPA>(#NAME), \
+                make_entry<shapes::NAME, VN_QUICK + VN_PLAIN>(#NAME), make_entry<shapes::NAME, VN_QUICK + VN_SC>(#NAME), \
+                make_entry<shapes::NAME, VN_QUICK + VN_2D>(#NAME),
 static const MsCyclicEntry kEntries[] = { CCGPU_LIST(X) };
 #undef X
 

@@ -55,6 +55,7 @@ struct MsParams {
   unsigned long long *work;      // dynamic frame queue head, zeroed by the host before the launch
   unsigned work_batch;            // most frame indices a warp takes from the queue per atomic (>= 1)
   unsigned work_shift;            // guided schedule: a warp takes min(work_batch, remaining >> work_shift) frames
+  int quick_hint;                 // host: enough all-positive frames are expected for the VN_QUICK kernels to pay
 };
 
 // counter slots (ccgpu_counters layout)
@@ -63,7 +64,9 @@ enum : int { C_FRAMES = 0, C_FRAME_ERR = 1, C_BIT_ERR = 2, C_ITER = 3, C_FAIL = 
 using ms_kernel_fn = void (*)(MsParams);
 
 // vertical-node flavour a kernel is compiled for
-enum : int { VN_PLAIN = 0 /* MS NMS OMS */, VN_SC = 1 /* SCMS1 SCMS2 */, VN_2D = 2 /* 2DNMS */, VN_SPA = 3 /* sum-product */, VN_COUNT = 4 };
+enum : int { VN_PLAIN = 0 /* MS NMS OMS */, VN_SC = 1 /* SCMS1 SCMS2 */, VN_2D = 2 /* 2DNMS */, VN_SPA = 3 /* sum-product */,
+             VN_QUICK = 4 /* + VN_PLAIN / VN_SC / VN_2D: the same with the all-positive-frame shortcut (ms_cyclic.cuh) */,
+             VN_COUNT = 7 };
 
 struct MsCyclicEntry {
   const char *name;

@@ -2,6 +2,7 @@
 (include/ccgpu.h via channelcoding_b200.engine); the checker is the oracle (oracle/*.c, pinned
 against the reference) and the committed golden vectors produced by the reference itself."""
 import math
+import os
 import zlib
 
 import numpy as np
@@ -617,3 +618,52 @@ def test_uncoded_point(ctx):
         y = ctx.awgn_llr(n, np.float32(cc.sigma(0.5, eb)), seed=3, point=9, frame0=17, frames=frames)
         neg = y < 0
         assert c["frames"] == frames and c["bit_errors"] == int(neg.sum()) and c["frame_errors"] == int(neg.any(axis=1).sum())
+
+
+@pytest.mark.parametrize("name,ebno", [("bch_15_7", 6.0), ("bch_31_16", 6.5), ("bch_63_36", 7.0), ("bch_63_57", 8.0),
+                                       ("bch_127_64", 7.5), ("bch_255_131", 8.5)])
+def test_all_positive_shortcut_is_exact(ctx, name, ebno, catalogue):
+    """frames whose channel values are all positive are decided without executing iteration 0 when the totals L are
+    not requested (ms_cyclic.cuh): same bits / iteration index / failure flag as the full path (L requested) and as
+    the oracle, for every flavour and stop rule; zeros, infinities and NaNs never take the shortcut wrongly"""
+    e = catalogue[name]
+    code = make_code(ctx, e)
+    n = e["n"]
+    rng = np.random.default_rng(zlib.crc32(("quick" + name).encode()))
+    frames = 6000 if n < 255 else 1500
+    y = (1 + oracle.sigma(e["rate"], ebno) * rng.standard_normal((frames, n))).astype(np.float32)
+    y[0] = 1.0
+    y[1, 3] = 0.0            # a zero is not positive
+    y[2] = np.inf
+    y[3, 5] = np.nan
+    y[4] = np.float32(1e-45)  # the smallest subnormal is positive
+    y[5, n - 1] = -0.0
+    allpos = (y > 0).all(axis=1)
+    assert 0.2 < allpos.mean() < 0.98   # both kinds of frames are present
+    for variant, alpha, beta, mi, stop in (("MS", 1, 0, 50, 0), ("NMS", 0.8, 0, 50, 0), ("OMS", 1, 0.3, 20, 0),
+                                           ("SCMS1", 1, 0, 30, 1), ("SCMS2", 1, 0, 50, 0), ("2DNMS", 0.9, 0.8, 25, 1),
+                                           ("NMS", 0.8, 0, 1, 0), ("MS", 1, 0, 5, 2)):
+        full = code.decode(y, variant, alpha, beta, mi, stop, want_L=True)
+        os.environ["CCGPU_QUICK"] = "1"   # the QUICK instantiation (normally chosen by ccgpu_awgn_point at high Eb/N0)
+        try:
+            fast = code.decode(y, variant, alpha, beta, mi, stop, want_L=False)
+        finally:
+            del os.environ["CCGPU_QUICK"]
+        assert fast[1] is None
+        what = "%s %s stop=%d" % (name, variant, stop)
+        assert np.array_equal(fast[0], full[0]) and np.array_equal(fast[2], full[2]) and np.array_equal(fast[3], full[3]), what
+        if stop != 2:
+            ok = allpos & ~np.isnan(y).any(axis=1)
+            assert not fast[0][ok].any() and not fast[2][ok].any() and not fast[3][ok].any(), what
+    hi = 1500 if n < 255 else 60
+    ob, _, oi, of = oracle.min_sum(code.H(), y[6:hi], "NMS", 0.8, 0.0, 50, 0)   # (the rows with inf / nan left out)
+    os.environ["CCGPU_QUICK"] = "1"
+    try:
+        fast = code.decode(y[6:hi], "NMS", 0.8, 0.0, 50, 0, want_L=False)
+        c1 = code.awgn_point(ebno, 300000 if n < 255 else 60000, "NMS", 0.8, seed=3, point=1)
+        os.environ["CCGPU_QUICK"] = "0"
+        c0 = code.awgn_point(ebno, 300000 if n < 255 else 60000, "NMS", 0.8, seed=3, point=1)
+    finally:
+        del os.environ["CCGPU_QUICK"]
+    assert np.array_equal(fast[0], ob) and np.array_equal(fast[2].astype(np.uint32), oi) and np.array_equal(fast[3], of)
+    assert c0 == c1   # fused Monte-Carlo point: identical counters with and without the shortcut
