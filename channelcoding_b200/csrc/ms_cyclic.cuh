@@ -558,11 +558,13 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VNQ>()) ms_cyclic
           if (p.failed) p.failed[my_frame] = failed ? 1 : 0;
 #if CCGPU_MS_SMEM_COUNTERS
           cnt_s[0][threadIdx.x] += 1u;
-          cnt_s[1][threadIdx.x] += (failed || nbits != 0) ? 1u : 0u;
-          cnt_s[2][threadIdx.x] += static_cast<unsigned>(nbits);
           cnt_s[3][threadIdx.x] += static_cast<unsigned>(it + 1);
-          cnt_s[4][threadIdx.x] += failed ? 1u : 0u;
-          cnt_s[5][threadIdx.x] += (!failed && nbits != 0) ? 1u : 0u;
+          if (failed || nbits != 0) {  // the error statistics: rare at the Eb/N0 where most frames are simulated
+            cnt_s[1][threadIdx.x] += 1u;
+            cnt_s[2][threadIdx.x] += static_cast<unsigned>(nbits);
+            cnt_s[4][threadIdx.x] += failed ? 1u : 0u;
+            cnt_s[5][threadIdx.x] += failed ? 0u : 1u;
+          }
 #else
           cnt_frames += 1;
           cnt_iter += static_cast<unsigned>(it + 1);
