@@ -268,6 +268,47 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VNQ>()) ms_cyclic
   }
   __syncwarp();
 
+  // dynamic schedule: every finishing group (`done`, warp-uniform when FPW == 1) gets the next frame index of the
+  // warp's pool, which is refilled from the global queue head with ONE atomic per batch of up to work_batch frames
+  // (one atomic per frame on one address capped the small codes); returns the index in every lane of the group
+  auto take_frames = [&](bool done) -> long long {
+    long long next = 0;
+    if (FPW == 1) {
+      if (done && lane == 0) {
+        int left = pool_left_s[warp_in_cta];
+        next = pool_next_s[warp_in_cta];
+        if (left == 0) {
+          left = static_cast<int>(guided_batch(p, next, pool_batch_s[warp_in_cta]));
+          pool_batch_s[warp_in_cta] = static_cast<unsigned>(left);
+          next = units + static_cast<long long>(atomicAdd(p.work, static_cast<unsigned long long>(left)));
+        }
+        pool_next_s[warp_in_cta] = next + 1;
+        pool_left_s[warp_in_cta] = left - 1;
+      }
+    } else {
+      const unsigned leadm = __ballot_sync(kFull, done && is_lead);
+      if (lane == 0) {
+        int left = pool_left_s[warp_in_cta], slot = 0;
+        long long nx = pool_next_s[warp_in_cta];
+        for (unsigned m = leadm; m; m &= m - 1u, ++slot) {
+          if (left == 0) {
+            left = static_cast<int>(guided_batch(p, nx, pool_batch_s[warp_in_cta]));
+            pool_batch_s[warp_in_cta] = static_cast<unsigned>(left);
+            nx = units + static_cast<long long>(atomicAdd(p.work, static_cast<unsigned long long>(left)));
+          }
+          grant_s[warp_in_cta][slot] = nx++;
+          --left;
+        }
+        pool_next_s[warp_in_cta] = nx;
+        pool_left_s[warp_in_cta] = left;
+      }
+      __syncwarp();
+      if (done && is_lead) next = grant_s[warp_in_cta][__popc(leadm & ((1u << lane) - 1u))];
+      __syncwarp();  // grant_s may be rewritten by the next call
+    }
+    return __shfl_sync(kFull, next, lead_lane);
+  };
+
   // QUICK flavour: a frame whose channel values are all positive is decided by iteration 0 without executing it --
   // q = y > 0 on every edge, so every check-node message is >= 0, every total L_c = S_c + y_c > 0, the decided word is
   // all-zero and both stop rules hold (soft_decision.h:161-202 with r = 0, S = 0).  The outputs are the same (bits 0,
@@ -575,42 +616,7 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VNQ>()) ms_cyclic
 #endif
         }
       }
-      // dynamic schedule: every finishing group gets the next frame index of the warp's pool, which is refilled from
-      // the global queue head with ONE atomic per work_batch frames (one atomic per frame on one address caps the
-      // queue at 1.5e9 frames/s, measured; the small codes decode several times faster than that)
-      if (FPW == 1) {
-        if (fin && lane == 0) {  // fin is warp uniform here: one group per warp
-          int left = pool_left_s[warp_in_cta];
-          next = pool_next_s[warp_in_cta];
-          if (left == 0) {
-            left = static_cast<int>(guided_batch(p, next, pool_batch_s[warp_in_cta]));
-            pool_batch_s[warp_in_cta] = static_cast<unsigned>(left);
-            next = units + static_cast<long long>(atomicAdd(p.work, static_cast<unsigned long long>(left)));
-          }
-          pool_next_s[warp_in_cta] = next + 1;
-          pool_left_s[warp_in_cta] = left - 1;
-        }
-      } else {
-        const unsigned leadm = __ballot_sync(kFull, fin && is_lead);
-        if (lane == 0) {
-          int left = pool_left_s[warp_in_cta], slot = 0;
-          long long nx = pool_next_s[warp_in_cta];
-          for (unsigned m = leadm; m; m &= m - 1u, ++slot) {
-            if (left == 0) {
-              left = static_cast<int>(guided_batch(p, nx, pool_batch_s[warp_in_cta]));
-              pool_batch_s[warp_in_cta] = static_cast<unsigned>(left);
-              nx = units + static_cast<long long>(atomicAdd(p.work, static_cast<unsigned long long>(left)));
-            }
-            grant_s[warp_in_cta][slot] = nx++;
-            --left;
-          }
-          pool_next_s[warp_in_cta] = nx;
-          pool_left_s[warp_in_cta] = left;
-        }
-        __syncwarp();
-        if (fin && is_lead) next = grant_s[warp_in_cta][__popc(leadm & ((1u << lane) - 1u))];
-      }
-      next = __shfl_sync(kFull, next, lead_lane);
+      next = take_frames(fin);
       if (fin) {
         my_frame = next;
         active = my_frame < static_cast<long long>(p.frames);
