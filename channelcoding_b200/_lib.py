@@ -16,8 +16,9 @@ class CcgpuError(RuntimeError):
 
 
 class MsParams(C.Structure):
-    _fields_ = [("variant", C.c_int32), ("stop_rule", C.c_int32), ("max_iter", C.c_uint32), ("reserved", C.c_uint32),
-                ("alpha", C.c_double), ("beta", C.c_double)]
+    _fields_ = [("variant", C.c_int32), ("stop_rule", C.c_int32), ("max_iter", C.c_uint32), ("q_msg_max", C.c_uint32),
+                ("alpha", C.c_double), ("beta", C.c_double), ("q_scale", C.c_double), ("q_y_max", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class Counters(C.Structure):
@@ -93,7 +94,7 @@ def lib():
     L.ccgpu_gf_decode_erasures.argtypes = [vp, vp, vp, u64, vp, vp, u32, vp, vp, vp]
     L.ccgpu_gf_decode_erasures_pgz.argtypes = [vp, vp, vp, u64, vp, vp, u32, vp, vp, vp]
     L.ccgpu_code_set_recheck.argtypes = [vp, i32]
-    if L.ccgpu_abi_version() != 1:
+    if L.ccgpu_abi_version() != 2:
         raise ImportError("libccgpu.so ABI version mismatch")
     _lib = L
     return L

@@ -57,6 +57,7 @@ struct ccgpu_code {
   int grid_max[VN_COUNT] = {};
   size_t smem[VN_COUNT] = {};
   bool all_columns_covered = false;
+  unsigned max_col_weight = 0;
   MsCsrDevice csr;     // general-H kernel tables (device)
   GfDevice gf;         // algebraic decoder tables (device)
 };
@@ -349,6 +350,15 @@ bool columns_covered(const CodeSpec &s) {
   }
   return true;
 }
+unsigned max_column_weight(const CodeSpec &s) {
+  unsigned best = 0;
+  for (unsigned c = 0; c < s.n; ++c) {
+    unsigned w = 0;
+    for (unsigned r = 0; r < s.rows; ++r) w += s.H[size_t(r) * s.n + c] != 0;
+    best = std::max(best, w);
+  }
+  return best;
+}
 
 // channel + hard decision (codes/codes.h:43-52: bit = y < 0): one thread = one Philox block = four symbols
 __global__ void __launch_bounds__(kAwgnThreads) awgn_hard_kernel(uint8_t *__restrict__ words, uint32_t n, float sigma,
@@ -428,6 +438,7 @@ int finish_code(ccgpu_ctx *ctx, ccgpu_code *c) {
   c->ctx = ctx;
   c->shape = analyse_H(c->spec.H.data(), c->spec.rows, c->spec.n);
   c->all_columns_covered = columns_covered(c->spec);
+  c->max_col_weight = max_column_weight(c->spec);
   if (!ctx) return CCGPU_OK;  // host-only description: no device tables, no decoding
   select_cyclic(c);
   int rc = ms_csr_upload(c->spec.H.data(), c->spec.rows, c->spec.n, &c->csr);
@@ -441,10 +452,50 @@ int finish_code(ccgpu_ctx *ctx, ccgpu_code *c) {
 
 int check_params(ccgpu_ctx *ctx, const ccgpu_ms_params *p) {
   if (!p) return fail(ctx, CCGPU_ERR_INVALID, "params is null");
-  if (p->variant < CCGPU_MS || p->variant > CCGPU_SPA) return fail(ctx, CCGPU_ERR_INVALID, "unknown variant");
+  if (p->variant < CCGPU_MS || p->variant > CCGPU_OMS_Q) return fail(ctx, CCGPU_ERR_INVALID, "unknown variant");
   if (p->stop_rule < 0 || p->stop_rule > CCGPU_STOP_NONE) return fail(ctx, CCGPU_ERR_INVALID, "unknown stop rule");
   if (p->max_iter < 1 || p->max_iter > 255) return fail(ctx, CCGPU_ERR_INVALID, "max_iter must be in 1..255");
-  if (p->variant == CCGPU_OMS && !(p->beta >= 0.0)) return fail(ctx, CCGPU_ERR_INVALID, "OMS needs beta >= 0");
+  if ((p->variant == CCGPU_OMS || p->variant == CCGPU_OMS_Q) && !(p->beta >= 0.0)) return fail(ctx, CCGPU_ERR_INVALID, "OMS needs beta >= 0");
+  return CCGPU_OK;
+}
+
+bool is_fixed(int variant) { return variant >= CCGPU_MS_Q && variant <= CCGPU_OMS_Q; }
+
+// the quantiser of the fixed-point variants with its defaults filled in (include/ccgpu.h)
+struct QuantSpec {
+  float scale;
+  int ymax, mmax, A, B;
+};
+QuantSpec quant_spec(const ccgpu_ms_params *p) {
+  QuantSpec q;
+  q.scale = static_cast<float>(p->q_scale > 0.0 ? p->q_scale : 8.0);
+  q.ymax = static_cast<int>(p->q_y_max ? p->q_y_max : 31u);
+  q.mmax = static_cast<int>(p->q_msg_max ? p->q_msg_max : 31u);
+  q.A = p->variant == CCGPU_NMS_Q ? static_cast<int>(std::lrint(p->alpha * 1024.0)) : 1024;
+  q.B = p->variant == CCGPU_OMS_Q ? static_cast<int>(std::lrint(p->beta * static_cast<double>(q.scale))) : 0;
+  return q;
+}
+// fn_h of the fixed-point variants on the host (the bound of the device kernel is stated with it)
+int fixed_fn_h(const QuantSpec &q, int m) {
+  const long long t = static_cast<long long>(q.A) * m, fl = t >> 10, rem = t & 1023;
+  const long long v = fl + ((rem > 512 || (rem == 512 && (fl & 1))) ? 1 : 0);
+  return static_cast<int>(std::max<long long>(v - q.B, 0));
+}
+// the two-frames-per-lane kernel carries its integers in fp16 halves: everything must stay within +-2048
+int check_params_q(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p) {
+  if (!is_fixed(p->variant)) return CCGPU_OK;
+  if (p->variant == CCGPU_NMS_Q && !(p->alpha >= 0.0 && p->alpha <= 1.0))
+    return fail(ctx, CCGPU_ERR_UNSUPPORTED, "fixed-point NMS needs 0 <= alpha <= 1");
+  if (!(p->q_scale >= 0.0) || p->q_scale > 1e6) return fail(ctx, CCGPU_ERR_INVALID, "q_scale out of range");
+  const QuantSpec q = quant_spec(p);
+  if (q.mmax > 1023 || q.B > 1024 || q.ymax > 2047) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "fixed-point: q_msg_max <= 1023, q_y_max <= 2047, offset <= 1024 steps");
+  const long long bound = static_cast<long long>(c->max_col_weight) * fixed_fn_h(q, q.mmax) + q.ymax;
+  if (bound > 2048) {
+    char msg[200];
+    std::snprintf(msg, sizeof msg, "fixed-point: column weight %u x fn_h(q_msg_max) %d + q_y_max %d = %lld exceeds the 2048 the "
+                  "packed kernel represents exactly; lower q_msg_max / q_y_max", c->max_col_weight, fixed_fn_h(q, q.mmax), q.ymax, bound);
+    return fail(ctx, CCGPU_ERR_UNSUPPORTED, msg);
+  }
   return CCGPU_OK;
 }
 
@@ -461,6 +512,14 @@ void fill_decoder(MsParams &mp, const ccgpu_code *c, const ccgpu_ms_params *p) {
   // the reference's stop test passes iff every row's integer overlap with b is 0 mod 256; when every
   // column is covered by some row and all row weights are < 256 that is exactly "b is all-zero"
   mp.stop_simple = (p->stop_rule == CCGPU_STOP_REF_ZERO_OVERLAP && c->all_columns_covered && c->shape.max_row_weight < 256) ? 1 : 0;
+  if (is_fixed(p->variant)) {
+    const QuantSpec q = quant_spec(p);
+    mp.q_scale = q.scale;
+    mp.q_ymax = q.ymax;
+    mp.q_mmax = q.mmax;
+    mp.q_alpha = q.A;
+    mp.q_beta = q.B;
+  }
 }
 
 // launch the min-sum decoder for one batch described by mp (source/outputs already filled)
@@ -471,18 +530,24 @@ int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsP
   const int vn = (p->variant == CCGPU_SCMS1 || p->variant == CCGPU_SCMS2) ? VN_SC
                  : p->variant == CCGPU_NMS2D                             ? VN_2D
                  : p->variant == CCGPU_SPA                               ? VN_SPA
+                 : is_fixed(p->variant)                                  ? VN_FIX
                                                                          : VN_PLAIN;
+  if (vn == VN_FIX) {
+    if (!c->cyc[VN_FIX]) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "fixed-point min-sum runs on the shape-specialised cyclic kernels only");
+    const int rc = check_params_q(ctx, c, p);
+    if (rc) return rc;
+  }
   // the QUICK instantiation retires all-positive frames without iterating (ms_cyclic.cuh); it pays when such frames
   // are frequent, i.e. in Monte-Carlo points at high Eb/N0 (the hint is set by ccgpu_awgn_point; CCGPU_QUICK=0/1
   // overrides it for every path, which is how the parity tests drive both instantiations over the same inputs)
   if (const char *env = std::getenv("CCGPU_QUICK")) mp.quick_hint = std::atoi(env) != 0;
-  const int vq = (mp.quick_hint && vn != VN_SPA && mp.L == nullptr && p->stop_rule != CCGPU_STOP_NONE && c->cyc[vn + VN_QUICK] &&
+  const int vq = (mp.quick_hint && vn != VN_SPA && vn != VN_FIX && mp.L == nullptr && p->stop_rule != CCGPU_STOP_NONE && c->cyc[vn + VN_QUICK] &&
                   c->cyc[vn] && c->cyc[vn + VN_QUICK]->k == c->cyc[vn]->k && c->cyc[vn + VN_QUICK]->fpw == 1)
                      ? vn + VN_QUICK
                      : vn;
   if (c->cyc[vq]) {
     const MsCyclicEntry *e = c->cyc[vq];
-    const uint64_t per_cta = e->cta ? 1 : uint64_t(kMsThreads / 32) * e->fpw;
+    const uint64_t per_cta = (e->cta ? 1 : uint64_t(kMsThreads / 32) * e->fpw) * e->slots;
     const uint64_t want = (mp.frames + per_cta - 1) / per_cta;
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(want, c->grid_max[vq]));
     CU(cudaMemsetAsync(work, 0, sizeof(unsigned long long), stream));
@@ -719,6 +784,7 @@ int ccgpu_code_set_rows(ccgpu_code *code, uint32_t rows) {
   }
   code->shape = analyse_H(code->spec.H.data(), code->spec.rows, code->spec.n);
   code->all_columns_covered = columns_covered(code->spec);
+  code->max_col_weight = max_column_weight(code->spec);
   if (!ctx) return CCGPU_OK;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);

@@ -1,7 +1,8 @@
 // ms_cyclic_inst.cu -- compiled once per -DCCGPU_GROUP=g: instantiates ms_cyclic_kernel for the
-// shapes of CCGPU_MS_LIST_g (ms_shapes_generated.h), four message-update flavours each plus the three QUICK ones, and
+// shapes of CCGPU_MS_LIST_g (ms_shapes_generated.h), four message-update flavours each plus the three QUICK ones and the fixed-point kernel (ms_cyclic_q.cuh), and
 // exposes them to the registry in ms_registry.cu.
 #include "ms_cyclic.cuh"
+#include "ms_cyclic_q.cuh"
 #include "ms_shapes_generated.h"
 
 #ifndef CCGPU_GROUP
@@ -23,14 +24,18 @@ template <class S> struct TapTable {
 template <class S> static const TapTable<S> kTapTable{};
 
 template <class S, int VN> MsCyclicEntry make_entry(const char *name) {
-  return MsCyclicEntry{ name, S::N, S::K, S::W, S::RPL, S::FPW, S::NP, S::WRAP ? 1 : 0, VN, kMsThreads, 0, kTapTable<S>.v,
+  return MsCyclicEntry{ name, S::N, S::K, S::W, S::RPL, S::FPW, S::NP, S::WRAP ? 1 : 0, VN, kMsThreads, 0, 1, kTapTable<S>.v,
                         reinterpret_cast<ms_kernel_fn>(&ms_cyclic_kernel<S, VN>) };
+}
+template <class S> MsCyclicEntry make_q_entry(const char *name) {
+  return MsCyclicEntry{ name, S::N, S::K, S::W, S::RPL, S::FPW, S::NP, S::WRAP ? 1 : 0, VN_FIX, kMsThreads, 0, 2, kTapTable<S>.v,
+                        reinterpret_cast<ms_kernel_fn>(&ms_cyclic_q_kernel<S>) };
 }
 
 #define X(NAME) make_entry<shapes::NAME, VN_PLAIN>(#NAME), make_entry<shapes::NAME, VN_SC>(#NAME), \
                 make_entry<shapes::NAME, VN_2D>(#NAME), make_entry<shapes::NAME, VN_SPA>(#NAME), \
                 make_entry<shapes::NAME, VN_QUICK + VN_PLAIN>(#NAME), make_entry<shapes::NAME, VN_QUICK + VN_SC>(#NAME), \
-                make_entry<shapes::NAME, VN_QUICK + VN_2D>(#NAME),
+                make_entry<shapes::NAME, VN_QUICK + VN_2D>(#NAME), make_q_entry<shapes::NAME>(#NAME),
 static const MsCyclicEntry kEntries[] = { CCGPU_LIST(X) };
 #undef X
 

@@ -8,7 +8,8 @@ constexpr int kMaxTaps = 128;      // row weight limit of the cyclic kernels
 constexpr int kMsThreads = 128;    // threads per CTA of the cyclic kernels (4 warps)
 constexpr int kCounterSlots = 8;   // ccgpu_counters as 8 x u64
 
-enum : int { V_MS = 0, V_NMS = 1, V_OMS = 2, V_SCMS1 = 3, V_SCMS2 = 4, V_NMS2D = 5, V_SPA = 6 };
+enum : int { V_MS = 0, V_NMS = 1, V_OMS = 2, V_SCMS1 = 3, V_SCMS2 = 4, V_NMS2D = 5, V_SPA = 6,
+             V_MS_Q = 7, V_NMS_Q = 8, V_OMS_Q = 9 /* fixed-point min-sum (ms_cyclic_q.cuh) */ };
 enum : int { STOP_REF = 0, STOP_GF2 = 1, STOP_NONE = 2 };
 enum : int { SRC_HBM = 0, SRC_PHILOX = 1, SRC_BITFLIP = 2 };
 
@@ -56,6 +57,10 @@ struct MsParams {
   unsigned work_batch;            // most frame indices a warp takes from the queue per atomic (>= 1)
   unsigned work_shift;            // guided schedule: a warp takes min(work_batch, remaining >> work_shift) frames
   int quick_hint;                 // host: enough all-positive frames are expected for the VN_QUICK kernels to pay
+  // ---- fixed-point variants (V_*_Q): y_int = clamp(rint(y * q_scale), +-q_ymax); messages saturate at q_mmax;
+  // fn_h(m) = max(rne(q_alpha * m / 1024) - q_beta, 0)
+  float q_scale;
+  int32_t q_ymax, q_mmax, q_alpha, q_beta;
 };
 
 // counter slots (ccgpu_counters layout)
@@ -66,13 +71,14 @@ using ms_kernel_fn = void (*)(MsParams);
 // vertical-node flavour a kernel is compiled for
 enum : int { VN_PLAIN = 0 /* MS NMS OMS */, VN_SC = 1 /* SCMS1 SCMS2 */, VN_2D = 2 /* 2DNMS */, VN_SPA = 3 /* sum-product */,
              VN_QUICK = 4 /* + VN_PLAIN / VN_SC / VN_2D: the same with the all-positive-frame shortcut (ms_cyclic.cuh) */,
-             VN_COUNT = 7 };
+             VN_FIX = 7 /* fixed-point min-sum, two frames per lane (ms_cyclic_q.cuh) */, VN_COUNT = 8 };
 
 struct MsCyclicEntry {
   const char *name;
   int n, k /* 0: rows at run time */, w, rpl, fpw, np, wrap, vn;
   int threads;  // CTA size
   int cta;      // 0: ms_cyclic_kernel (warp owns frames), 1: ms_cyclic_cta_kernel (CTA owns one frame)
+  int slots;    // frames a lane / thread works on at once (2 for the fixed-point kernels, else 1)
   const int *taps;
   ms_kernel_fn fn;
 };

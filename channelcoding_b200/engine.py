@@ -11,7 +11,7 @@ import numpy as np
 from . import _lib
 from ._lib import CcgpuError, CodeInfo, Counters, MsParams
 
-VARIANTS = {"MS": 0, "NMS": 1, "OMS": 2, "SCMS1": 3, "SCMS2": 4, "2DNMS": 5, "SPA": 6}
+VARIANTS = {"MS": 0, "NMS": 1, "OMS": 2, "SCMS1": 3, "SCMS2": 4, "2DNMS": 5, "SPA": 6, "MS_Q": 7, "NMS_Q": 8, "OMS_Q": 9}
 STOP_REF_ZERO_OVERLAP, STOP_GF2_PARITY, STOP_NONE = 0, 1, 2
 CAP_ERRORS, CAP_DMIN = 0, 1
 
@@ -30,9 +30,11 @@ def _ptr(x):
     return x.ctypes.data
 
 
-def ms_params(variant="MS", alpha=1.0, beta=0.0, max_iter=50, stop_rule=STOP_REF_ZERO_OVERLAP):
+def ms_params(variant="MS", alpha=1.0, beta=0.0, max_iter=50, stop_rule=STOP_REF_ZERO_OVERLAP, quant=None):
+    """quant: (q_scale, q_y_max, q_msg_max) of the fixed-point variants MS_Q / NMS_Q / OMS_Q; None = the defaults (8, 31, 31)"""
     v = VARIANTS[variant] if isinstance(variant, str) else int(variant)
-    return MsParams(v, int(stop_rule), int(max_iter), 0, float(alpha), float(beta))
+    qs, qy, qm = quant if quant is not None else (0.0, 0, 0)
+    return MsParams(v, int(stop_rule), int(max_iter), int(qm), float(alpha), float(beta), float(qs), int(qy), 0)
 
 
 def _check(ctx, rc):
@@ -199,9 +201,9 @@ class Code:
 
     # ---- decoding
     def decode(self, y, variant="MS", alpha=1.0, beta=0.0, max_iter=50, stop_rule=STOP_REF_ZERO_OVERLAP, want_L=True,
-               out=None):
+               out=None, quant=None):
         """min_sum<float,uint8_t>(H, y, Tag{}) per frame -> bits, L, iter, failed (ccgpu_decode_llr)"""
-        p = ms_params(variant, alpha, beta, max_iter, stop_rule)
+        p = ms_params(variant, alpha, beta, max_iter, stop_rule, quant)
         if _is_torch(y):
             import torch
             y = y.contiguous().view(-1, self.n)
@@ -228,10 +230,10 @@ class Code:
         return bits, L, it, failed
 
     def awgn_point(self, ebno_db, frames, variant="MS", alpha=1.0, beta=0.0, max_iter=50,
-                   stop_rule=STOP_REF_ZERO_OVERLAP, seed=0, point=0, frame0=0, out=None):
+                   stop_rule=STOP_REF_ZERO_OVERLAP, seed=0, point=0, frame0=0, out=None, quant=None):
         """one Eb/N0 point of awgn_simulation (simulation.c++:112-149), fused on the GPU -> counters.
         out: optional torch uint64/int64 CUDA tensor of 8 slots that is accumulated into (no sync)."""
-        p = ms_params(variant, alpha, beta, max_iter, stop_rule)
+        p = ms_params(variant, alpha, beta, max_iter, stop_rule, quant)
         if out is not None:
             self.ctx._check(_lib.lib().ccgpu_awgn_point(self.ctx._h, self._h, C.byref(p), float(ebno_db), seed, point,
                                                         frame0, frames, _ptr(out)))
@@ -282,9 +284,9 @@ class Code:
         return c.as_dict()
 
     def bitflip_point(self, weight, variant="MS", alpha=1.0, beta=0.0, max_iter=50,
-                      stop_rule=STOP_REF_ZERO_OVERLAP, first=0, count=0):
+                      stop_rule=STOP_REF_ZERO_OVERLAP, first=0, count=0, quant=None):
         """one error weight of bitflip_simulation (simulation.c++:156-213) -> counters"""
-        p = ms_params(variant, alpha, beta, max_iter, stop_rule)
+        p = ms_params(variant, alpha, beta, max_iter, stop_rule, quant)
         c = Counters()
         self.ctx._check(_lib.lib().ccgpu_bitflip_point(self.ctx._h, self._h, C.byref(p), weight, first, count,
                                                        C.addressof(c)))

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define CCGPU_ABI_VERSION 1
+#define CCGPU_ABI_VERSION 2 /* 2: ccgpu_ms_params grew the fixed-point fields; ccgpu_group_*; packed outputs */
 
 typedef struct ccgpu_ctx ccgpu_ctx;
 typedef struct ccgpu_code ccgpu_code;
@@ -53,7 +53,23 @@ typedef enum {
   CCGPU_SCMS1 = 3, /* self_correcting_1_min_sum_tag "SCMS1" :52-56, :256-268                           */
   CCGPU_SCMS2 = 4, /* self_correcting_2_min_sum_tag "SCMS2" :58-62, :270-282                           */
   CCGPU_NMS2D = 5, /* normalized_2d_min_sum_tag    "2DNMS" :64-73, :284-295   r = alpha*min, q = beta*e + y */
-  CCGPU_SPA = 6    /* sum-product (tanh rule); extension, not in the reference                         */
+  CCGPU_SPA = 6,   /* sum-product (tanh rule); extension, not in the reference                         */
+  /* FIXED-POINT min-sum; extension, not in the reference (its decoders are float32): min_sum__ of
+   * soft_decision.h:161-202 with integer messages, restated in oracle/ms_oracle.c (oracle_min_sum_fixed):
+   *   y_i = clamp(rint(y * q_scale), -q_y_max, +q_y_max)      float32 product, ties to even, NaN -> 0
+   *   q   = (S_c - r) + y_c                                   exact (wide accumulators, :135-136)
+   *   r   = sign * fn_h(min(min_{others} |q|, q_msg_max))     three-valued signum as :75-77, :106-118
+   *   L_c = S_c + y_c, b_c = L_c < 0, stop rules as for the float variants
+   * with fn_h(m) = m (MS_Q), rne(A m / 1024), A = rint(alpha * 1024) (NMS_Q, ties to even),
+   * max(m - B, 0), B = rint(beta * q_scale) (OMS_Q).  Hard decisions, iteration indices and failure flags are
+   * bit-identical to that restatement; `L` returns the integer totals (units of 1 / q_scale) as floats.
+   * The device kernel decodes TWO frames per lane in the 16-bit halves of every register (exact integer
+   * arithmetic on the fp16x2 pipe) and therefore needs
+   *   max_column_weight * fn_h(q_msg_max) + q_y_max <= 2048,  q_msg_max <= 1023,  alpha <= 1,  B <= 1024;
+   * other parameter sets are rejected with CCGPU_ERR_UNSUPPORTED.  Cyclic (BCH) parity-check matrices only. */
+  CCGPU_MS_Q = 7,
+  CCGPU_NMS_Q = 8,
+  CCGPU_OMS_Q = 9
 } ccgpu_variant;
 
 /* ---- stop rules ------------------------------------------------------------ */
@@ -69,9 +85,12 @@ typedef struct {
   int32_t variant;    /* ccgpu_variant */
   int32_t stop_rule;  /* ccgpu_stop_rule */
   uint32_t max_iter;  /* template parameter Iterations of the reference's tags (50 in benchmark.c++) */
-  uint32_t reserved;
+  uint32_t q_msg_max; /* fixed-point variants: check-node messages saturate at +-q_msg_max; 0 = default 31 */
   double alpha;       /* NMS / 2DNMS scale  (std::ratio parameter of the tag) */
   double beta;        /* OMS offset / 2DNMS variable-node scale; must be >= 0 for OMS */
+  double q_scale;     /* fixed-point variants: quantiser steps per unit of y; 0 = default 8 */
+  uint32_t q_y_max;   /* fixed-point variants: channel values saturate at +-q_y_max steps; 0 = default 31 */
+  uint32_t reserved;
 } ccgpu_ms_params;
 
 /* error / iteration counters of one Monte-Carlo batch; all-zero codeword transmitted like

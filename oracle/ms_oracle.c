@@ -14,6 +14,10 @@
  *                 stop rules GF2_PARITY / NONE, runtime alpha/beta/max_iter outside the tag
  *                 instantiations of oracle/ref_shim.cc, and SPA (sum-product): PARITY UNPINNED
  *                 (no reference implementation exists; they reuse the pinned loop structure).
+ *                 Fixed-point min-sum (oracle_min_sum_fixed, variants MS_Q / NMS_Q / OMS_Q): PARITY UNPINNED --
+ *                 the reference has no integer decoder; the function below is min_sum__ with Q = R = int and
+ *                 is cross-checked against the pinned float decoder for a fine quantiser
+ *                 (tests/test_oracle_golden.py::test_fixed_point_converges_to_float).
  */
 #include <float.h>
 #include <math.h>
@@ -179,6 +183,135 @@ int oracle_min_sum_batch(const uint8_t *H, unsigned rows, unsigned cols, const f
     unsigned it = 0;
     int rc = oracle_min_sum(H, rows, cols, y + f * cols, variant, alpha, beta, max_iter, stop_rule,
                             bits + f * cols, L ? L + f * cols : 0, &it);
+    iter[f] = it;
+    failed[f] = (uint8_t)rc;
+  }
+  return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Fixed-point min-sum (north_star "fixed-point min-sum"; include/ccgpu.h CCGPU_MS_Q / NMS_Q / OMS_Q).
+ * PARITY UNPINNED: the reference has no integer instantiation.  This is min_sum__
+ * (soft_decision.h:161-202) with its loops, evaluation structure and three-valued signum kept and
+ * Q = R = int:
+ *   quantiser      y_i = clamp(rint(y * q_scale), -q_y_max, +q_y_max)   float32 product, ties to even,
+ *                  NaN -> 0 (the channel values enter the loop exactly once, here)
+ *   vertical__     q = (S_c - r) + y_c in wide accumulators (:135-136), no saturation
+ *   horizontal__   sign = prod signum(q_i), min = min |q_i| over the others (:106-116);
+ *                  r = sign * fn_h(min(min, q_msg_max))  -- the message saturates before fn_h
+ *                    MS_Q   fn_h(m) = m                                       (:204)
+ *                    NMS_Q  fn_h(m) = rne(A * m / 1024), A = rint(alpha*1024) (:211-213 in Q10)
+ *                    OMS_Q  fn_h(m) = max(m - B, 0),     B = rint(beta * q_scale)  (:245-251)
+ *   totals         L_c = S_c + y_c, b_c = L_c < 0 (:178-183), stop rules as above (:79-84)
+ * Integer addition is associative, so the summation order of column_sum is irrelevant here. */
+enum { V_MS_Q = 7, V_NMS_Q = 8, V_OMS_Q = 9 };
+
+static int signum_i(int v) { return (0 < v) - (v < 0); }
+
+int oracle_quantise(float y, float q_scale, int q_y_max) {
+  const float t = y * q_scale;
+  if (t != t) return 0;
+  if (t >= (float)q_y_max) return q_y_max;
+  if (t <= -(float)q_y_max) return -q_y_max;
+  return (int)lrintf(t); /* default rounding mode: to nearest, ties to even */
+}
+
+static long long rne_shift10(long long t) { /* t >= 0: round(t / 1024) to nearest, ties to even */
+  const long long fl = t >> 10, rem = t & 1023;
+  if (rem > 512 || (rem == 512 && (fl & 1))) return fl + 1;
+  return fl;
+}
+
+static int cn_value_fixed(int variant, int sign, int min, int q_msg_max, int A, int B) {
+  int m = min < q_msg_max ? min : q_msg_max;
+  if (variant == V_NMS_Q) m = (int)rne_shift10((long long)A * m);
+  else if (variant == V_OMS_Q) m = m - B > 0 ? m - B : 0;
+  return sign * m;
+}
+
+int oracle_min_sum_fixed(const uint8_t *H, unsigned rows, unsigned cols, const float *y, int variant,
+                         double alpha, double beta, unsigned max_iter, int stop_rule, float q_scale,
+                         int q_y_max, int q_msg_max, uint8_t *b_out, int32_t *L_out, unsigned *iter_out) {
+  const size_t E = (size_t)rows * cols;
+  int *q = (int *)calloc(E, sizeof(int));
+  int *r = (int *)calloc(E, sizeof(int));
+  int *yi = (int *)calloc(cols, sizeof(int));
+  int *col_sums = (int *)calloc(cols, sizeof(int));
+  int *L = (int *)calloc(cols, sizeof(int));
+  uint8_t *b = (uint8_t *)calloc(cols, 1);
+  const int A = (int)lrint(alpha * 1024.0), B = (int)lrint(beta * (double)q_scale);
+  int rc = 1;
+  unsigned iteration;
+  for (unsigned c = 0; c < cols; c++) yi[c] = oracle_quantise(y[c], q_scale, q_y_max);
+  for (iteration = 0; iteration < max_iter; iteration++) {
+    /* vertical__ (:125-140) */
+    for (unsigned c = 0; c < cols; c++) col_sums[c] = 0;
+    for (unsigned row = 0; row < rows; row++)
+      for (unsigned col = 0; col < cols; col++)
+        if (H[row * cols + col]) col_sums[col] += r[row * cols + col];
+    for (unsigned row = 0; row < rows; row++)
+      for (unsigned col = 0; col < cols; col++)
+        if (H[row * cols + col]) q[row * cols + col] = (col_sums[col] - r[row * cols + col]) + yi[col];
+    /* horizontal__ (:101-122) */
+    for (unsigned row = 0; row < rows; row++)
+      for (unsigned col = 0; col < cols; col++)
+        if (H[row * cols + col]) {
+          int sign = 1, min = INT32_MAX;
+          for (unsigned i = 0; i < cols; i++)
+            if (i != col && H[row * cols + i]) {
+              sign *= signum_i(q[row * cols + i]);
+              const int a = abs(q[row * cols + i]);
+              if (a < min) min = a;
+            }
+          r[row * cols + col] = cn_value_fixed(variant, sign, min, q_msg_max, A, B);
+        }
+    /* totals and hard decision (:178-183) */
+    for (unsigned c = 0; c < cols; c++) col_sums[c] = 0;
+    for (unsigned row = 0; row < rows; row++)
+      for (unsigned col = 0; col < cols; col++)
+        if (H[row * cols + col]) col_sums[col] += r[row * cols + col];
+    for (unsigned c = 0; c < cols; c++) {
+      L[c] = col_sums[c] + yi[c];
+      b[c] = (uint8_t)(L[c] < 0);
+    }
+    int stop = 0;
+    if (stop_rule == STOP_REF_ZERO_OVERLAP) {
+      stop = 1;
+      for (unsigned row = 0; row < rows && stop; row++) {
+        uint8_t acc = 0;
+        for (unsigned c = 0; c < cols; c++) acc = (uint8_t)(acc + H[row * cols + c] * b[c]);
+        if (acc) stop = 0;
+      }
+    } else if (stop_rule == STOP_GF2_PARITY) {
+      stop = 1;
+      for (unsigned row = 0; row < rows && stop; row++) {
+        unsigned acc = 0;
+        for (unsigned c = 0; c < cols; c++) acc ^= (unsigned)(H[row * cols + c] & b[c]);
+        if (acc) stop = 0;
+      }
+    } else {
+      stop = (iteration + 1 == max_iter);
+    }
+    if (stop) {
+      rc = 0;
+      break;
+    }
+  }
+  memcpy(b_out, b, cols);
+  if (L_out) memcpy(L_out, L, cols * sizeof(int32_t));
+  *iter_out = iteration;
+  free(q); free(r); free(yi); free(col_sums); free(L); free(b);
+  return rc;
+}
+
+int oracle_min_sum_fixed_batch(const uint8_t *H, unsigned rows, unsigned cols, const float *y, uint64_t frames,
+                               int variant, double alpha, double beta, unsigned max_iter, int stop_rule,
+                               float q_scale, int q_y_max, int q_msg_max, uint8_t *bits, int32_t *L,
+                               uint32_t *iter, uint8_t *failed) {
+  for (uint64_t f = 0; f < frames; f++) {
+    unsigned it = 0;
+    int rc = oracle_min_sum_fixed(H, rows, cols, y + f * cols, variant, alpha, beta, max_iter, stop_rule, q_scale,
+                                  q_y_max, q_msg_max, bits + f * cols, L ? L + f * cols : 0, &it);
     iter[f] = it;
     failed[f] = (uint8_t)rc;
   }

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liboracle.so")
 
 V_MS, V_NMS, V_OMS, V_SCMS1, V_SCMS2, V_NMS2D, V_SPA = range(7)
-VARIANTS = {"MS": 0, "NMS": 1, "OMS": 2, "SCMS1": 3, "SCMS2": 4, "2DNMS": 5, "SPA": 6}
+VARIANTS = {"MS": 0, "NMS": 1, "OMS": 2, "SCMS1": 3, "SCMS2": 4, "2DNMS": 5, "SPA": 6, "MS_Q": 7, "NMS_Q": 8, "OMS_Q": 9}
 STOP_REF_ZERO_OVERLAP, STOP_GF2_PARITY, STOP_NONE = 0, 1, 2
 FAM_BCH, FAM_RS = 0, 1
 
@@ -42,6 +42,10 @@ def lib():
         L = C.CDLL(_SO)
         L.oracle_min_sum_batch.argtypes = [_u8p, C.c_uint, C.c_uint, _f32p, C.c_uint64, C.c_int, C.c_double,
                                            C.c_double, C.c_uint, C.c_int, _u8p, C.c_void_p, _u32p, _u8p]
+        L.oracle_min_sum_fixed_batch.argtypes = [_u8p, C.c_uint, C.c_uint, _f32p, C.c_uint64, C.c_int, C.c_double,
+                                                 C.c_double, C.c_uint, C.c_int, C.c_float, C.c_int, C.c_int, _u8p,
+                                                 C.c_void_p, _u32p, _u8p]
+        L.oracle_quantise.argtypes = [C.c_float, C.c_float, C.c_int]
         L.oracle_gf_tables.argtypes = [C.c_uint, C.c_uint, _u16p, _u16p]
         L.oracle_code_new.restype = C.c_void_p
         L.oracle_code_new.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_uint, C.c_uint]
@@ -72,6 +76,22 @@ def min_sum(H, y, variant="MS", alpha=1.0, beta=0.0, max_iter=50, stop_rule=STOP
     failed = np.zeros(f, np.uint8)
     lib().oracle_min_sum_batch(H, H.shape[0], H.shape[1], y, f, v, alpha, beta, max_iter, stop_rule,
                                bits, L.ctypes.data, it, failed)
+    return bits, L, it, failed
+
+
+def min_sum_fixed(H, y, variant="MS_Q", alpha=1.0, beta=0.0, max_iter=50, stop_rule=STOP_REF_ZERO_OVERLAP, q_scale=8.0,
+                  q_y_max=31, q_msg_max=31):
+    """fixed-point min-sum (unpinned extension, ms_oracle.c) -> bits u8, L int32 (integer totals), iter u32, failed u8"""
+    H = np.ascontiguousarray(H, np.uint8)
+    y = np.ascontiguousarray(y, np.float32).reshape(-1, H.shape[1])
+    v = VARIANTS[variant] if isinstance(variant, str) else int(variant)
+    f = y.shape[0]
+    bits = np.zeros((f, H.shape[1]), np.uint8)
+    L = np.zeros((f, H.shape[1]), np.int32)
+    it = np.zeros(f, np.uint32)
+    failed = np.zeros(f, np.uint8)
+    lib().oracle_min_sum_fixed_batch(H, H.shape[0], H.shape[1], y, f, v, alpha, beta, max_iter, stop_rule,
+                                     float(q_scale), int(q_y_max), int(q_msg_max), bits, L.ctypes.data, it, failed)
     return bits, L, it, failed
 
 

@@ -22,7 +22,8 @@ def test_header_symbols_exported():
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.ccgpu_abi_version() == 1
+    assert L.ccgpu_abi_version() == 2
+    assert ctypes.sizeof(_lib.MsParams) == 48
 
 
 def test_no_device_is_loud():

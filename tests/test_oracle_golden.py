@@ -171,3 +171,38 @@ def test_pgz_erasure_rule_pinned_by_the_reference(catalogue):
         assert np.array_equal(status[clean], g[name + ".status"][clean]), name
         ok = clean & (status == 0)
         assert np.array_equal(out[ok], g[name + ".corrected"][ok]), name
+
+
+# ---- fixed-point restatement (unpinned extension): quantiser known answers and convergence to the pinned float decoder
+def test_fixed_point_quantiser_kat():
+    import ctypes as C
+    q = oracle.lib().oracle_quantise
+    q.restype = C.c_int
+    assert q(0.0625, 8.0, 31) == 0 and q(0.1875, 8.0, 31) == 2 and q(-0.1875, 8.0, 31) == -2  # ties to even
+    assert q(0.3125, 8.0, 31) == 2 and q(0.4375, 8.0, 31) == 4
+    assert q(100.0, 8.0, 31) == 31 and q(-100.0, 8.0, 31) == -31
+    assert q(float("inf"), 8.0, 31) == 31 and q(float("-inf"), 8.0, 31) == -31 and q(float("nan"), 8.0, 31) == 0
+    assert q(1.0, 8.0, 31) == 8 and q(-1.0, 3.0, 7) == -3
+
+
+def test_fixed_point_converges_to_float(catalogue):
+    """with a fine quantiser and no saturation the integer loop takes the float decoder's hard
+    decisions.  Stated disagreement: the decoder is chaotic on these dense matrices (a last-bit difference moves the
+    iteration at which the all-zero word appears), so the bar is on the DECISIONS of frames that converge in both
+    runs and on the word error rate, not on iteration indices."""
+    rng = np.random.default_rng(0)
+    for name, frames, eb in (("bch_15_7", 4000, 3.0), ("bch_63_36", 1500, 4.0)):
+        e = catalogue[name]
+        H = oracle.Code(0, e["q"], e["t"]).H()
+        y = (1 + oracle.sigma(e["rate"], eb) * rng.standard_normal((frames, e["n"]))).astype(np.float32)
+        fb, _, fi, ff = oracle.min_sum(H, y, "NMS", 0.8, 0.0, 50)
+        qb, _, qi, qf = oracle.min_sum_fixed(H, y, "NMS_Q", 0.8, 0.0, 50, 0, 65536.0, 1 << 24, 1 << 24)
+        both = (ff == 0) & (qf == 0)
+        assert both.mean() > 0.75
+        assert np.array_equal(fb[both], qb[both])  # under the reference stop rule both are the all-zero word
+        wer_f, wer_q = (ff | fb.any(axis=1)).mean(), (qf | qb.any(axis=1)).mean()
+        assert abs(wer_f - wer_q) < 3 * np.sqrt(wer_f * (1 - wer_f) / frames) + 0.01
+        # first-iteration decisions (no accumulated rounding yet) agree on every frame
+        f1 = oracle.min_sum(H, y, "NMS", 0.8, 0.0, 1, 2)
+        q1 = oracle.min_sum_fixed(H, y, "NMS_Q", 0.8, 0.0, 1, 2, 65536.0, 1 << 24, 1 << 24)
+        assert (f1[0] != q1[0]).mean() < 2e-4
