@@ -94,6 +94,23 @@ def lib():
     L.ccgpu_gf_decode_erasures.argtypes = [vp, vp, vp, u64, vp, vp, u32, vp, vp, vp]
     L.ccgpu_gf_decode_erasures_pgz.argtypes = [vp, vp, vp, u64, vp, vp, u32, vp, vp, vp]
     L.ccgpu_code_set_recheck.argtypes = [vp, i32]
+    cpp = C.POINTER(vp)
+    L.ccgpu_group_create.argtypes = [i32, C.POINTER(i32), C.POINTER(vp)]
+    L.ccgpu_group_destroy.argtypes = [vp]
+    L.ccgpu_group_destroy.restype = None
+    L.ccgpu_group_size.argtypes = [vp]
+    L.ccgpu_group_ctx.argtypes = [vp, i32]
+    L.ccgpu_group_ctx.restype = vp
+    L.ccgpu_group_last_error.argtypes = [vp]
+    L.ccgpu_group_last_error.restype = C.c_char_p
+    L.ccgpu_group_set_min_frames.argtypes = [vp, u64]
+    L.ccgpu_group_awgn_point.argtypes = [vp, cpp, C.POINTER(MsParams), dbl, u64, u32, u64, u64, vp]
+    L.ccgpu_group_awgn_point_hard.argtypes = [vp, cpp, dbl, u64, u32, u64, u64, vp]
+    L.ccgpu_group_awgn_point_mbbp.argtypes = [vp, cpp, C.POINTER(MsParams), vp, u32, dbl, u64, u32, u64, u64, vp]
+    L.ccgpu_group_awgn_point_uncoded.argtypes = [vp, u32, dbl, dbl, u64, u32, u64, u64, vp]
+    L.ccgpu_group_bitflip_point.argtypes = [vp, cpp, C.POINTER(MsParams), u32, u64, u64, vp]
+    L.ccgpu_group_decode_llr.argtypes = [vp, cpp, C.POINTER(MsParams), vp, u64, vp, vp, vp, vp]
+    L.ccgpu_group_gf_decode.argtypes = [vp, cpp, vp, u64, vp, vp, vp]
     if L.ccgpu_abi_version() != 2:
         raise ImportError("libccgpu.so ABI version mismatch")
     _lib = L
@@ -107,4 +124,7 @@ EXPORTS = ["ccgpu_abi_version", "ccgpu_create", "ccgpu_destroy", "ccgpu_last_err
            "ccgpu_code_to_string", "ccgpu_code_H", "ccgpu_code_H_alt", "ccgpu_code_poly", "ccgpu_gf_tables", "ccgpu_encode",
            "ccgpu_decode_llr", "ccgpu_sigma", "ccgpu_shannon_limit_db", "ccgpu_sweep_start_ebno", "ccgpu_sweep_samples", "ccgpu_awgn_llr", "ccgpu_awgn_point", "ccgpu_awgn_point_hard", "ccgpu_bitflip_point",
            "ccgpu_gf_decode", "ccgpu_gf_decode_erasures", "ccgpu_code_set_recheck", "ccgpu_decode_llr_mbbp", "ccgpu_awgn_point_uncoded", "ccgpu_gf_decode_erasures_pgz",
-           "ccgpu_awgn_point_mbbp"]
+           "ccgpu_awgn_point_mbbp", "ccgpu_group_create", "ccgpu_group_destroy", "ccgpu_group_size", "ccgpu_group_ctx",
+           "ccgpu_group_last_error", "ccgpu_group_set_min_frames", "ccgpu_group_awgn_point", "ccgpu_group_awgn_point_hard",
+           "ccgpu_group_awgn_point_mbbp", "ccgpu_group_awgn_point_uncoded", "ccgpu_group_bitflip_point",
+           "ccgpu_group_decode_llr", "ccgpu_group_gf_decode"]

@@ -31,7 +31,7 @@ def _groups():
 
 def _units():
     units = [("api.o", "api.cu", []), ("ms_registry.o", "ms_registry.cu", []), ("ms_csr.o", "ms_csr.cu", []),
-             ("gf_decode.o", "gf_decode.cu", [])]
+             ("gf_decode.o", "gf_decode.cu", []), ("group.o", "group.cc", [])]
     units.append(("ms_cyclic_cta.o", "ms_cyclic_cta_inst.cu", []))
     for g in range(_groups()):
         units.append(("ms_cyclic_g%d.o" % g, "ms_cyclic_inst.cu", ["-DCCGPU_GROUP=%d" % g]))
@@ -39,7 +39,7 @@ def _units():
 
 
 def _deps():
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".hpp", ".cuh", ".cu"))]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".hpp", ".cuh", ".cu", ".cc"))]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "ccgpu.h"))
     deps.append(os.path.abspath(__file__))
     return deps
@@ -69,7 +69,7 @@ def build(force=False, verbose=False):
         f.write("\n".join(logs))
     if verbose:
         print("\n".join(logs))
-    cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + [os.path.join(OBJ, u[0]) for u in units]
+    cmd = [NVCC] + ARCH + ["-shared", "-Xcompiler", "-pthread", "-o", LIB] + [os.path.join(OBJ, u[0]) for u in units]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)

@@ -1,4 +1,5 @@
 // api.cu -- the extern "C" boundary of libccgpu.so (include/ccgpu.h) and the host-side launch logic.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -519,6 +520,11 @@ void fill_decoder(MsParams &mp, const ccgpu_code *c, const ccgpu_ms_params *p) {
     mp.q_mmax = q.mmax;
     mp.q_alpha = q.A;
     mp.q_beta = q.B;
+    auto splat = [](float v) { return 0x10001u * static_cast<uint32_t>(__half_as_ushort(__float2half_rn(v))); };  // exact values
+    mp.q_h2_mmax = splat(static_cast<float>(q.mmax));
+    mp.q_h2_alpha = splat(static_cast<float>(q.A) / 1024.0f);
+    mp.q_h2_1024 = splat(1024.0f);
+    mp.q_h2_1024b = splat(static_cast<float>(1024 + q.B));
   }
 }
 
@@ -540,6 +546,9 @@ int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsP
   // the QUICK instantiation retires all-positive frames without iterating (ms_cyclic.cuh); it pays when such frames
   // are frequent, i.e. in Monte-Carlo points at high Eb/N0 (the hint is set by ccgpu_awgn_point; CCGPU_QUICK=0/1
   // overrides it for every path, which is how the parity tests drive both instantiations over the same inputs)
+  // the fixed-point kernels test for all-positive frames at run time when the hint is set; with several frames per
+  // warp all of them must be all-positive at once, which is rare: measured slower there (profiles/r2_notes.md)
+  if (vn == VN_FIX && c->cyc[VN_FIX] && !c->cyc[VN_FIX]->cta && c->cyc[VN_FIX]->fpw != 1) mp.quick_hint = 0;
   if (const char *env = std::getenv("CCGPU_QUICK")) mp.quick_hint = std::atoi(env) != 0;
   const int vq = (mp.quick_hint && vn != VN_SPA && vn != VN_FIX && mp.L == nullptr && p->stop_rule != CCGPU_STOP_NONE && c->cyc[vn + VN_QUICK] &&
                   c->cyc[vn] && c->cyc[vn + VN_QUICK]->k == c->cyc[vn]->k && c->cyc[vn + VN_QUICK]->fpw == 1)
@@ -1050,6 +1059,13 @@ int ccgpu_awgn_point(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_para
     // measured on BCH(63,36): the QUICK kernel is 3.5 % slower at 4 dB (5 % such frames), 7 % faster at 6 dB (35 %),
     // 27 % faster at 7 dB (59 %), 50 % faster at 8 dB (78 %); shapes with several frames per warp do not gain
     mp.quick_hint = std::pow(1.0 - q, static_cast<double>(code->spec.n)) >= 0.25 ? 1 : 0;
+    if (is_fixed(params->variant)) {
+      // fixed point: "positive" is decided after quantisation (y * scale rounds to >= 1); the two-slot kernel skips an
+      // iteration only when BOTH slots hold such frames: measured to pay from about half of the frames on
+      const QuantSpec qs = quant_spec(params);
+      const double qq = 0.5 * std::erfc((1.0 - 0.5 / qs.scale) / (static_cast<double>(mp.sigma) * std::sqrt(2.0)));
+      mp.quick_hint = std::pow(1.0 - qq, static_cast<double>(code->spec.n)) >= 0.5 ? 1 : 0;
+    }
   }
   mp.point = point;
   mp.frame0 = frame0;

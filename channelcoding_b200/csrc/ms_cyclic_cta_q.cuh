@@ -81,64 +81,92 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_q_min_blocks<S>()) ms_cycli
     ybuf[c] = 0u;
     sbuf[c] = 0u;
   }
-  const unsigned kMmax = h2_splat(p.q_mmax);
-  const unsigned kAlpha = 0x10001u * __half_as_ushort(__float2half_rn(static_cast<float>(p.q_alpha) * (1.0f / 1024.0f)));
-  const unsigned k1024 = h2_splat(1024);
-  const unsigned k1024B = h2_splat(1024 + p.q_beta);
-  const unsigned kOne = h2_splat(1);
+  const unsigned kMmax = p.q_h2_mmax, kAlpha = p.q_h2_alpha, k1024 = p.q_h2_1024, k1024B = p.q_h2_1024b;  // fp16x2, host-made
+  const bool quick_ok = p.quick_hint != 0 && p.L == nullptr && p.stop_rule != STOP_NONE && p.max_iter >= 1;
   __syncthreads();
 
   while (active[0] || active[1]) {
-    // ---------------- (re)fill
+    // ---------------- (re)fill; fresh frames whose quantised channel values are all positive are retired on the spot
+    // (decided by iteration 0 without executing it, see ms_cyclic_q.cuh)
+    while (true) {
+      const bool need[2] = { active[0] && need_init[0], active[1] && need_init[1] };  // block-uniform
+      if (!need[0] && !need[1]) break;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      if (!(active[h] && need_init[h])) continue;  // block-uniform
-      if (p.src == SRC_HBM) {
-        for (int c = tid; c < N; c += THREADS) {
-          const unsigned short v = quantise_h(__ldg(p.y + frame[h] * N + c), p.q_scale, p.q_ymax);
-          ybuf16[2 * c + h] = v;
-          sbuf16[2 * c + h] = v;
-        }
-      } else if (p.src == SRC_PHILOX) {
-        for (int b = tid; b < NBLK; b += THREADS) {
-          const float4 v = awgn_block(p.keys, p.point, p.frame0 + static_cast<uint64_t>(frame[h]), b, p.sigma);
-          const float vv[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-          for (int e = 0; e < 4; ++e)
-            if (4 * b + e < N) {
-              const unsigned short q = quantise_h(vv[e], p.q_scale, p.q_ymax);
-              ybuf16[2 * (4 * b + e) + h] = q;
-              sbuf16[2 * (4 * b + e) + h] = q;
-            }
-        }
-      } else if (tid == 0) {
-        unsigned long long rank = p.frame0 + static_cast<unsigned long long>(frame[h]);
-        unsigned ones = p.flip_weight;
-        const unsigned short plus = quantise_h(1.0f, p.q_scale, p.q_ymax), minus = quantise_h(-1.0f, p.q_scale, p.q_ymax);
-        for (int c = 0; c < N; ++c) {
-          const unsigned long long zero_first = binom(N - c - 1, ones);
-          unsigned short v = plus;
-          if (rank >= zero_first && ones > 0) {
-            rank -= zero_first;
-            --ones;
-            v = minus;
+      for (int h = 0; h < 2; ++h) {
+        if (!need[h]) continue;
+        if (p.src == SRC_HBM) {
+          for (int c = tid; c < N; c += THREADS) {
+            const unsigned short v = quantise_h(__ldg(p.y + frame[h] * N + c), p.q_scale, p.q_ymax);
+            ybuf16[2 * c + h] = v;
+            sbuf16[2 * c + h] = v;
           }
-          ybuf16[2 * c + h] = v;
-          sbuf16[2 * c + h] = v;
+        } else if (p.src == SRC_PHILOX) {
+          for (int b = tid; b < NBLK; b += THREADS) {
+            const float4 v = awgn_block(p.keys, p.point, p.frame0 + static_cast<uint64_t>(frame[h]), b, p.sigma);
+            const float vv[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (4 * b + e < N) {
+                const unsigned short q = quantise_h(vv[e], p.q_scale, p.q_ymax);
+                ybuf16[2 * (4 * b + e) + h] = q;
+                sbuf16[2 * (4 * b + e) + h] = q;
+              }
+          }
+        } else if (tid == 0) {
+          unsigned long long rank = p.frame0 + static_cast<unsigned long long>(frame[h]);
+          unsigned ones = p.flip_weight;
+          const unsigned short plus = quantise_h(1.0f, p.q_scale, p.q_ymax), minus = quantise_h(-1.0f, p.q_scale, p.q_ymax);
+          for (int c = 0; c < N; ++c) {
+            const unsigned long long zero_first = binom(N - c - 1, ones);
+            unsigned short v = plus;
+            if (rank >= zero_first && ones > 0) {
+              rank -= zero_first;
+              --ones;
+              v = minus;
+            }
+            ybuf16[2 * c + h] = v;
+            sbuf16[2 * c + h] = v;
+          }
         }
+        const unsigned keep = h == 0 ? 0xffff0000u : 0x0000ffffu;
+#pragma unroll
+        for (int i = 0; i < RPL; ++i)
+#pragma unroll
+          for (int j = 0; j < W; ++j) r[i][j] &= keep;
+        it[h] = 0;
+        need_init[h] = false;
       }
-      const unsigned keep = h == 0 ? 0xffff0000u : 0x0000ffffu;
+      __syncthreads();
+      if (!quick_ok) break;
+      bool again = false;
 #pragma unroll
-      for (int i = 0; i < RPL; ++i)
-#pragma unroll
-        for (int j = 0; j < W; ++j) r[i][j] &= keep;
-      it[h] = 0;
-      need_init[h] = false;
+      for (int h = 0; h < 2; ++h) {
+        if (!need[h]) continue;
+        bool allpos = true;
+        for (int c = tid; c < N; c += THREADS) allpos &= static_cast<short>(ybuf16[2 * c + h]) > 0;
+        if (!__syncthreads_and(allpos)) continue;  // block-uniform
+        if (p.bits)
+          for (int c = tid; c < N; c += THREADS) p.bits[frame[h] * N + c] = 0;
+        if (tid == 0) {
+          if (p.iter) p.iter[frame[h]] = 0;
+          if (p.failed) p.failed[frame[h]] = 0;
+          cnt[C_FRAMES] += 1;
+          cnt[C_ITER] += 1;
+          s_next[h] = units + static_cast<long long>(atomicAdd(p.work, 1ull));
+        }
+        __syncthreads();
+        frame[h] = s_next[h];
+        active[h] = frame[h] < static_cast<long long>(p.frames);
+        need_init[h] = true;
+        again = true;
+      }
+      if (!again) break;
+      __syncthreads();  // s_next is rewritten by the next round
     }
-    __syncthreads();
+    if (!active[0] && !active[1]) break;
 
     // ---------------- VN + CN, both slots (see ms_cyclic_q.cuh)
-    unsigned f2s[RPL], ds[RPL], m1n[RPL];
+    unsigned f2s[RPL], ds[RPL], m1v[RPL];
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
       unsigned m1 = 0x7bff7bffu, m2 = 0x7bff7bffu, par = 0;
@@ -158,15 +186,14 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_q_min_blocks<S>()) ms_cycli
       const unsigned f1 = g1 ^ (par & SIGN2), f2 = g2 ^ (par & SIGN2);
       f2s[i] = f2;
       ds[i] = h2_sub(f1, f2);
-      m1n[i] = h2_neg(m1);
+      m1v[i] = m1;
     }
 #pragma unroll
     for (int i = 0; i < RPL; ++i)
 #pragma unroll
       for (int j = 0; j < W; ++j) {
         const unsigned q = r[i][j];
-        const unsigned t = h2_min(h2_add(h2_abs(q), m1n[i]), kOne);
-        r[i][j] = h2_fma(ds[i], t, f2s[i]) ^ (q & SIGN2);
+        r[i][j] = h2_fma(ds[i], h2_gt_abs(q, m1v[i]), f2s[i]) ^ (q & SIGN2);
       }
 
     // ---------------- column sums: warp-private partials, then one reduction over the warps

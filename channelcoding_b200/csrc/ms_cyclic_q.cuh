@@ -19,9 +19,9 @@
 //     (S'_c = y_c + sum_rows r, so q = S' - r and L = S': one load and one add per edge less than the float
 //     kernel), and the order of the column sum does not matter (only its read-modify-write hazard is kept in
 //     program order, as in ms_cyclic.cuh).
-//   * the "min over the others" select is arithmetic: t = min(|q| - min1, 1) is 0 exactly on the edge(s) that
-//     attain min1 (integers), r = f2 - (f2 - f1) * t; that moves two instructions per edge from the saturated
-//     alu pipe (compare + select) to the fma pipe.
+//   * the "min over the others" select is arithmetic: t = (|q| > min1) as 1.0 / 0.0 per half (one HSET2.BF) is 0 exactly
+//     on the edge(s) that attain min1, r = f2 + (f1 - f2) * t (one HFMA2, exact on integers): per-half predicates do
+//     not exist, and a mask + two LOP3 would all sit on the alu pipe, the busiest one.
 #pragma once
 #include <cstdint>
 #include <cuda_fp16.h>
@@ -70,6 +70,12 @@ __device__ __forceinline__ unsigned h2_neg(unsigned a) {
   asm("neg.f16x2 %0, %1;" : "=r"(d) : "r"(a));
   return d;
 }
+// per half: |a| > b ? 1.0 : 0.0  (HSET2.BF.GT with the |a| operand modifier)
+__device__ __forceinline__ unsigned h2_gt_abs(unsigned a, unsigned b) {
+  unsigned d;
+  asm("{.reg .b32 t; abs.f16x2 t, %1; set.gt.f16x2.f16x2 %0, t, %2;}" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
 __device__ __forceinline__ unsigned short int_to_h(int v) { return __half_as_ushort(__int2half_rn(v)); }
 __device__ __forceinline__ unsigned h2_splat(int v) { return 0x10001u * int_to_h(v); }
 
@@ -81,9 +87,18 @@ __device__ __forceinline__ unsigned short quantise_h(float y, float scale, int y
   return int_to_h(v);  // 0 -> +0
 }
 
+#ifndef CCGPU_Q_HSET
+#define CCGPU_Q_HSET 1  /* argmin select through HSET2.BF (1) or min(|q| - min1, 1) (0) */
+#endif
+#ifndef CCGPU_Q_QUICK
+#define CCGPU_Q_QUICK 1  /* compile the all-positive shortcut into the refill loop */
+#endif
+#ifndef CCGPU_Q_MINBLK
+#define CCGPU_Q_MINBLK 8  /* resident CTAs per SM the small shapes (<= 22 packed messages per lane) are compiled for */
+#endif
 template <class S> constexpr int ms_q_min_blocks() {
   // packed messages per lane -> resident CTAs per SM the register allocation aims at (64 / 102 / 168 registers)
-  return S::RPL * S::W <= 22 ? 8 : S::RPL * S::W <= 40 ? 5 : S::RPL * S::W <= 72 ? 3 : 1;
+  return S::RPL * S::W <= 22 ? CCGPU_Q_MINBLK : S::RPL * S::W <= 40 ? 5 : S::RPL * S::W <= 72 ? 3 : 1;
 }
 
 template <class S>
@@ -249,44 +264,61 @@ __global__ void __launch_bounds__(kMsThreads, ms_q_min_blocks<S>()) ms_cyclic_q_
   //   g = max(rne(A m / 1024) - B, 0) with (A, B) = (1024, 0) MS_Q, (A, 0) NMS_Q, (1024, B) OMS_Q.
   // fma(m, A/1024, 1024) rounds the exact sum ONCE to the fp16 grid, whose spacing is 1 in [1024, 2048): that is
   // rne(A m / 1024) + 1024 (m <= q_msg_max <= 1023, A <= 1024; A/1024 is a fp16 number)
-  const unsigned kMmax = h2_splat(p.q_mmax);
-  const unsigned kAlpha = 0x10001u * __half_as_ushort(__float2half_rn(static_cast<float>(p.q_alpha) * (1.0f / 1024.0f)));
-  const unsigned k1024 = h2_splat(1024);
-  const unsigned k1024B = h2_splat(1024 + p.q_beta);
-  const unsigned kOne = h2_splat(1);
+  const unsigned kMmax = p.q_h2_mmax, kAlpha = p.q_h2_alpha, k1024 = p.q_h2_1024, k1024B = p.q_h2_1024b;  // fp16x2, host-made
   unsigned short *const ybuf16 = reinterpret_cast<unsigned short *>(ybuf);
   unsigned short *const sbuf16 = reinterpret_cast<unsigned short *>(sbuf);
+  // the all-positive shortcut needs no totals (L is only known after the column sums) and a stop rule
+  const bool quick_ok = CCGPU_Q_QUICK && p.quick_hint != 0 && p.L == nullptr && p.stop_rule != STOP_NONE && p.max_iter >= 1;
 
   while (true) {
     if (__ballot_sync(kFull, active[0] || active[1]) == 0u) break;
 
-    // ============ (re)fill the slots that finished
+    // ============ (re)fill the slots that finished.  Both slots of a lane are served by ONE pass (for BCH(63,36) the 2 x 16
+    // Philox blocks of two frames keep all 32 lanes busy).  A fresh frame whose quantised channel values are all
+    // positive is decided by iteration 0: q = y > 0 on every edge, so every check-node message is >= 0, every total
+    // L = y + sum r > 0, the decided word is all-zero and both stop rules hold (soft_decision.h:161-202 with r = 0).
+    // When every active slot of the warp holds such a frame the iteration is skipped -- same outputs (bits 0,
+    // iteration index 0, no failure, one iteration counted).  At high Eb/N0, where a sweep spends most of its frames,
+    // that is the common case (a retirement loop inside the refill measured 15 % slower at 4 dB: code growth).
+    bool skip = false;
+    while (true) {  // (one pass; `break` leaves it)
+      bool need[2];
+      unsigned initm[2];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const unsigned initm = __ballot_sync(kFull, active[h] && need_init[h]);
-      if (initm == 0u) continue;
+      for (int h = 0; h < 2; ++h) {
+        need[h] = active[h] && need_init[h];
+        initm[h] = __ballot_sync(kFull, need[h]);
+      }
+      if ((initm[0] | initm[1]) == 0u) break;
       __syncwarp();  // the finished frame's totals were read by other lanes (outputs)
       if (p.src == SRC_HBM) {
 #pragma unroll
-        for (int ps = 0; ps < NP; ++ps) {
-          const long long fr = __shfl_sync(kFull, my_frame[h], cgrp_lead[ps]);
-          if (cvalid[ps] && ((initm >> cgrp_lead[ps]) & 1u)) {
-            const unsigned short v = quantise_h(__ldg(p.y + fr * N + ccol[ps]), p.q_scale, p.q_ymax);
-            ybuf16[2 * (lane + 32 * ps) + h] = v;
-            sbuf16[2 * (lane + 32 * ps) + h] = v;
+        for (int h = 0; h < 2; ++h) {
+          if (initm[h] == 0u) continue;
+#pragma unroll
+          for (int ps = 0; ps < NP; ++ps) {
+            const long long fr = __shfl_sync(kFull, my_frame[h], cgrp_lead[ps]);
+            if (cvalid[ps] && ((initm[h] >> cgrp_lead[ps]) & 1u)) {
+              const unsigned short v = quantise_h(__ldg(p.y + fr * N + ccol[ps]), p.q_scale, p.q_ymax);
+              ybuf16[2 * (lane + 32 * ps) + h] = v;
+              sbuf16[2 * (lane + 32 * ps) + h] = v;
+            }
           }
         }
       } else if (p.src == SRC_PHILOX) {
+        constexpr int PER_SLOT = FPW * NBLK;  // Philox blocks of one slot of this warp
 #pragma unroll
-        for (int b0 = 0; b0 < FPW * NBLK; b0 += 32) {
+        for (int b0 = 0; b0 < 2 * PER_SLOT; b0 += 32) {
           const int b = b0 + lane;
-          const bool bv = b < FPW * NBLK;
-          const int f = (FPW > 1 && bv) ? b / NBLK : 0;
-          const int blk = b - f * NBLK;
+          const bool bv = b < 2 * PER_SLOT;
+          const int h = (bv && b >= PER_SLOT) ? 1 : 0;
+          const int bb = b - h * PER_SLOT;
+          const int f = (FPW > 1 && bv) ? bb / NBLK : 0;
+          const int blk = bb - f * NBLK;
           const int src_lane = f * k;
-          const long long fr = __shfl_sync(kFull, my_frame[h], src_lane);
-          if (bv && ((initm >> src_lane) & 1u)) {
-            const float4 v = awgn_block(p.keys, p.point, p.frame0 + static_cast<uint64_t>(fr), blk, p.sigma);
+          const long long fr0 = __shfl_sync(kFull, my_frame[0], src_lane), fr1 = __shfl_sync(kFull, my_frame[1], src_lane);
+          if (bv && (((h ? initm[1] : initm[0]) >> src_lane) & 1u)) {
+            const float4 v = awgn_block(p.keys, p.point, p.frame0 + static_cast<uint64_t>(h ? fr1 : fr0), blk, p.sigma);
             const int c0 = f * N + 4 * blk;
             const float vv[4] = { v.x, v.y, v.z, v.w };
 #pragma unroll
@@ -299,37 +331,68 @@ __global__ void __launch_bounds__(kMsThreads, ms_q_min_blocks<S>()) ms_cyclic_q_
           }
         }
       } else {  // SRC_BITFLIP
-        if (is_lead && active[h] && need_init[h]) {
-          unsigned long long rank = p.frame0 + static_cast<unsigned long long>(my_frame[h]);
-          unsigned ones = p.flip_weight;
-          const unsigned short plus = quantise_h(1.0f, p.q_scale, p.q_ymax), minus = quantise_h(-1.0f, p.q_scale, p.q_ymax);
-          for (int c = 0; c < N; ++c) {
-            const unsigned long long zero_first = binom(N - c - 1, ones);
-            unsigned short v = plus;
-            if (rank >= zero_first && ones > 0) {
-              rank -= zero_first;
-              --ones;
-              v = minus;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (is_lead && need[h]) {
+            unsigned long long rank = p.frame0 + static_cast<unsigned long long>(my_frame[h]);
+            unsigned ones = p.flip_weight;
+            const unsigned short plus = quantise_h(1.0f, p.q_scale, p.q_ymax), minus = quantise_h(-1.0f, p.q_scale, p.q_ymax);
+            for (int c = 0; c < N; ++c) {
+              const unsigned long long zero_first = binom(N - c - 1, ones);
+              unsigned short v = plus;
+              if (rank >= zero_first && ones > 0) {
+                rank -= zero_first;
+                --ones;
+                v = minus;
+              }
+              ybuf16[2 * (colbase + c) + h] = v;
+              sbuf16[2 * (colbase + c) + h] = v;
             }
-            ybuf16[2 * (colbase + c) + h] = v;
-            sbuf16[2 * (colbase + c) + h] = v;
           }
         }
       }
-      if (active[h] && need_init[h]) {
-        const unsigned keep = h == 0 ? 0xffff0000u : 0x0000ffffu;  // zero this slot's messages (+0)
+      {
+        const unsigned keep = (need[0] ? 0u : 0x0000ffffu) | (need[1] ? 0u : 0xffff0000u);  // zero the fresh slots' messages (+0)
 #pragma unroll
         for (int i = 0; i < RPL; ++i)
 #pragma unroll
           for (int j = 0; j < W; ++j) r[i][j] &= keep;
-        it[h] = 0;
-        need_init[h] = false;
       }
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        if (need[h]) {
+          it[h] = 0;
+          need_init[h] = false;
+        }
       __syncwarp();
+      // ---- all-positive fresh frames: if every active slot of this warp holds one, the iteration is not executed
+      if (quick_ok) {
+        bool mine_quick = true;  // my group's active slots are fresh and all-positive
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          unsigned nonpos = 0;
+          if (initm[h] != 0u) {
+#pragma unroll
+            for (int ps = 0; ps < NP; ++ps) {
+              const short v = static_cast<short>(ybuf16[2 * (lane + 32 * ps) + h]);  // fp16 pattern: <= 0 as an integer iff the value is <= 0
+              nonpos |= __ballot_sync(kFull, cvalid[ps] && v <= 0) & cmask[ps];
+            }
+          }
+          if (active[h] && !(need[h] && nonpos == 0u)) mine_quick = false;
+        }
+        skip = __all_sync(kFull, mine_quick);
+      }
+      break;
     }
-
+    unsigned bw[2][NP];
+    bool fin[2], stopv[2];
+    if (skip) {
+#pragma unroll
+      for (int ps = 0; ps < NP; ++ps) bw[0][ps] = bw[1][ps] = 0u;
+      stopv[0] = stopv[1] = true;
+    } else {
     // ============ VN + CN for both slots at once (vertical__ / horizontal__)
-    unsigned f2s[RPL], ds[RPL], m1n[RPL];
+    unsigned f2s[RPL], ds[RPL], m1v[RPL];
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
       unsigned m1 = 0x7bff7bffu, m2 = 0x7bff7bffu;  // largest finite fp16 = "numeric_limits::max()" (:107)
@@ -352,14 +415,18 @@ __global__ void __launch_bounds__(kMsThreads, ms_q_min_blocks<S>()) ms_cyclic_q_
       const unsigned f2 = g2 ^ (par & SIGN2);
       f2s[i] = f2;
       ds[i] = h2_sub(f1, f2);   // f1 - f2: r = f2 + (f1 - f2) * t
-      m1n[i] = h2_neg(m1);
+      m1v[i] = m1;
     }
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
 #pragma unroll
       for (int j = 0; j < W; ++j) {
         const unsigned q = r[i][j];
-        const unsigned t = h2_min(h2_add(h2_abs(q), m1n[i]), kOne);  // 0 on the argmin edge(s), else 1 (integers)
+#if CCGPU_Q_HSET
+        const unsigned t = h2_gt_abs(q, m1v[i]);  // 0.0 on the edge(s) attaining min1, else 1.0
+#else
+        const unsigned t = h2_min(h2_sub(h2_abs(q), m1v[i]), 0x3c003c00u);
+#endif
         const unsigned f = h2_fma(ds[i], t, f2s[i]);
         r[i][j] = f ^ (q & SIGN2);  // times the sign of the edge's own q: product of the OTHER signs (:114,:118)
       }
@@ -391,7 +458,6 @@ __global__ void __launch_bounds__(kMsThreads, ms_q_min_blocks<S>()) ms_cyclic_q_
     if (VOLCS) __syncwarp();
 
     // ============ totals L = S', hard decision (:178-183), stop test (:79-84), per slot
-    unsigned bw[2][NP];
 #pragma unroll
     for (int ps = 0; ps < NP; ++ps) {
       // L < 0 is the sign bit: a total is never -0 (y enters as +0, x - x = +0, +0 + -0 = +0 in round-to-nearest)
@@ -399,7 +465,6 @@ __global__ void __launch_bounds__(kMsThreads, ms_q_min_blocks<S>()) ms_cyclic_q_
       bw[0][ps] = __ballot_sync(kFull, (x & 0x8000u) != 0u);
       bw[1][ps] = __ballot_sync(kFull, (x & 0x80000000u) != 0u);
     }
-    bool fin[2], stopv[2];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       bool stop;
@@ -425,8 +490,10 @@ __global__ void __launch_bounds__(kMsThreads, ms_q_min_blocks<S>()) ms_cyclic_q_
         stop = (badm & gmask) == 0u;
       }
       stopv[h] = stop;
-      fin[h] = active[h] && (stop || it[h] + 1 >= p.max_iter);
     }
+    }  // !skip
+#pragma unroll
+    for (int h = 0; h < 2; ++h) fin[h] = active[h] && (stopv[h] || it[h] + 1 >= p.max_iter);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const unsigned finm = __ballot_sync(kFull, fin[h]);

@@ -61,6 +61,9 @@ struct MsParams {
   // fn_h(m) = max(rne(q_alpha * m / 1024) - q_beta, 0)
   float q_scale;
   int32_t q_ymax, q_mmax, q_alpha, q_beta;
+  // the same constants as fp16x2 words (both halves equal), converted on the host so that a kernel that has to
+  // rematerialise them inside its loop pays one constant-bank read, not an integer -> fp16 conversion
+  uint32_t q_h2_mmax, q_h2_alpha /* q_alpha / 1024 */, q_h2_1024 /* 1024 */, q_h2_1024b /* 1024 + q_beta */;
 };
 
 // counter slots (ccgpu_counters layout)

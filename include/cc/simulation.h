@@ -59,10 +59,7 @@ class decoder {
     // hard-decision tags: channel, hard decision (codes.h:43-52), algebraic decode and the error test of
     // simulation.c++:126-135 all on the device (ccgpu_awgn_point_hard)
     ccgpu_counters hard_point(double ebno_db, uint64_t frames, uint64_t seed, uint32_t point, uint64_t frame0) const {
-      ccgpu_counters c{};
-      implementation.ctx()->check(ccgpu_awgn_point_hard(implementation.ctx()->get(), implementation.handle(), ebno_db, seed,
-                                                        point, frame0, frames, &c));
-      return c;
+      return implementation.awgn_point_hard(ebno_db, frames, seed, point, frame0);
     }
     template <typename U = T>
     ccgpu_counters point_impl(double e, uint64_t f, uint64_t s, uint32_t p, uint64_t f0, std::true_type) const {
@@ -74,26 +71,36 @@ class decoder {
     }
     ccgpu_counters flips_impl(unsigned weight, std::true_type) const { return implementation.bitflip_point(weight); }
     ccgpu_counters flips_impl(unsigned weight, std::false_type) const {
-      // enumerate the patterns on the host (std::next_permutation order), decode in one batch
+      // enumerate the patterns on the host (std::next_permutation order like simulation.c++:181-199) and decode them
+      // in bounded chunks: C(127, 6) patterns would not fit any memory in one piece, the reference streams them too
       const unsigned n_ = T::n;
+      const size_t chunk = std::max<size_t>(1, (size_t(64) << 20) / n_);
       std::vector<int> b(n_ - weight, 0);
       b.insert(b.end(), weight, 1);
-      std::vector<uint8_t> w;
+      std::vector<uint8_t> w, out, failed;
+      w.reserve(chunk * n_);
+      ccgpu_counters c{};
+      auto flush = [&] {
+        const uint64_t count = w.size() / n_;
+        if (!count) return;
+        out.resize(w.size());
+        failed.resize(count);
+        implementation.correct_batch(w.data(), count, out.data(), failed.data());
+        for (uint64_t f = 0; f < count; ++f) {
+          unsigned bits = 0;
+          for (unsigned i = 0; i < n_; ++i) bits += out[f * n_ + i] != 0;
+          c.frames++;
+          c.failures += failed[f];
+          c.bit_errors += bits;
+          c.frame_errors += (failed[f] || bits) ? 1 : 0;
+        }
+        w.clear();
+      };
       do {
         for (int bit : b) w.push_back(static_cast<uint8_t>(bit));
+        if (w.size() >= chunk * n_) flush();
       } while (std::next_permutation(b.begin(), b.end()));
-      const uint64_t count = w.size() / n_;
-      std::vector<uint8_t> out(w.size()), failed(count);
-      implementation.correct_batch(w.data(), count, out.data(), failed.data());
-      ccgpu_counters c{};
-      for (uint64_t f = 0; f < count; ++f) {
-        unsigned bits = 0;
-        for (unsigned i = 0; i < n_; ++i) bits += out[f * n_ + i] != 0;
-        c.frames++;
-        c.failures += failed[f];
-        c.bit_errors += bits;
-        c.frame_errors += (failed[f] || bits) ? 1 : 0;
-      }
+      flush();
       return c;
     }
   public:

@@ -286,6 +286,43 @@ int ccgpu_gf_decode_erasures_pgz(ccgpu_ctx *ctx, const ccgpu_code *code, const u
  * erasure-free words the check is implied by "deg Lambda <= t and deg Lambda distinct roots" (DESIGN.md 4). */
 int ccgpu_code_set_recheck(ccgpu_code *code, int enable);
 
+/* ---- device groups: several GPUs of one host behind one handle --------------------------------------------------
+ * Replaces nothing in the reference (it has no device); it is where simulation.c++:112-149 decides how much work a
+ * point is and waits for its word-error rate (:91-93 sizes the next point from it).  A group owns one context per
+ * member device.  A sharded call splits the global unit range [first, first + units) (frames, patterns, words)
+ * into contiguous parts, member m running the ordinary single-device entry point on its part from its own host
+ * thread and stream, and merges the results inside the library: the eight counters are summed on the host
+ * (the noise is keyed by the GLOBAL frame index, so the counters are identical for any number of devices);
+ * batched decodes write disjoint slices of the caller's host buffers.  Ranges smaller than
+ * ccgpu_group_set_min_frames (default 16384) per member use fewer members.  Codes are per device: `codes[m]` must
+ * have been created on ccgpu_group_ctx(group, m) with the same parameters.  One group call runs at a time. */
+typedef struct ccgpu_group ccgpu_group;
+/* devices == NULL: CUDA ordinals 0 .. n_devices-1 */
+int ccgpu_group_create(int n_devices, const int *devices, ccgpu_group **out);
+void ccgpu_group_destroy(ccgpu_group *group);
+int ccgpu_group_size(const ccgpu_group *group);
+ccgpu_ctx *ccgpu_group_ctx(const ccgpu_group *group, int member);
+const char *ccgpu_group_last_error(const ccgpu_group *group);
+int ccgpu_group_set_min_frames(ccgpu_group *group, uint64_t frames_per_member);
+/* the Monte-Carlo points of ccgpu_awgn_point / _hard / _mbbp / _uncoded / ccgpu_bitflip_point, sharded; `out` is a
+ * host pointer and holds the merged counters on return */
+int ccgpu_group_awgn_point(ccgpu_group *group, ccgpu_code *const *codes, const ccgpu_ms_params *params, double ebno_db,
+                           uint64_t seed, uint32_t point, uint64_t frame0, uint64_t frames, ccgpu_counters *out);
+int ccgpu_group_awgn_point_hard(ccgpu_group *group, ccgpu_code *const *codes, double ebno_db, uint64_t seed, uint32_t point,
+                                uint64_t frame0, uint64_t frames, ccgpu_counters *out);
+int ccgpu_group_awgn_point_mbbp(ccgpu_group *group, ccgpu_code *const *codes, const ccgpu_ms_params *params,
+                                const uint32_t *shifts, uint32_t n_bases, double ebno_db, uint64_t seed, uint32_t point,
+                                uint64_t frame0, uint64_t frames, ccgpu_counters *out);
+int ccgpu_group_awgn_point_uncoded(ccgpu_group *group, uint32_t n, double rate, double ebno_db, uint64_t seed, uint32_t point,
+                                   uint64_t frame0, uint64_t frames, ccgpu_counters *out);
+int ccgpu_group_bitflip_point(ccgpu_group *group, ccgpu_code *const *codes, const ccgpu_ms_params *params, uint32_t weight,
+                              uint64_t first, uint64_t count, ccgpu_counters *out);
+/* ccgpu_decode_llr / ccgpu_gf_decode with HOST buffers, frames / words sharded over the members */
+int ccgpu_group_decode_llr(ccgpu_group *group, ccgpu_code *const *codes, const ccgpu_ms_params *params, const float *y,
+                           uint64_t frames, uint8_t *bits, float *L, uint8_t *iter, uint8_t *failed);
+int ccgpu_group_gf_decode(ccgpu_group *group, ccgpu_code *const *codes, const uint8_t *words, uint64_t count,
+                          uint8_t *corrected, uint8_t *n_errors, uint8_t *failed);
+
 #ifdef __cplusplus
 }
 #endif

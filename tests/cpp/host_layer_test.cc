@@ -8,6 +8,7 @@
 #include <fstream>
 #include <iostream>
 #include <sstream>
+#include <cstdlib>
 
 #include "cc/simulation.h"
 
@@ -35,6 +36,15 @@ static int host_tests() {
   CHECK(normalized_2d_min_sum_tag<50>::to_string() == "2DNMS");
   CHECK(berlekamp_massey_tag::to_string() == "BM" && euklid_tag::to_string() == "EUKLID" &&
         peterson_gorenstein_zierler_tag::to_string() == "PGZ");
+  // extension tags: fixed-point min-sum
+  CHECK((fixed_normalized_min_sum_tag<50, std::ratio<8, 10> >::to_string() == "NMSQ") && fixed_min_sum_tag<>::to_string() == "MSQ");
+  {
+    const ccgpu_ms_params p = detail::params_of<fixed_offset_min_sum_tag<20, std::ratio<1, 4>, fixed_point<16, 63, 40> > >::get(stop_rule::gf2_parity);
+    CHECK(p.variant == CCGPU_OMS_Q && p.max_iter == 20 && p.beta == 0.25 && p.q_scale == 16.0 && p.q_y_max == 63 && p.q_msg_max == 40 &&
+          p.stop_rule == CCGPU_STOP_GF2_PARITY);
+    const ccgpu_ms_params f = detail::params_of<min_sum_tag<50> >::get(stop_rule::reference);
+    CHECK(f.q_scale == 0.0 && f.q_y_max == 0 && f.q_msg_max == 0);
+  }
   CHECK((normalized_min_sum_tag<50, std::ratio<8, 10> >::alpha == 0.8));
   CHECK((offset_min_sum_tag<50, std::ratio<1, 100> >::beta == 0.01));
   // the reference's 2DNMS default is alpha = beta = 1 (soft_decision.h:71)
@@ -218,8 +228,78 @@ static int gpu_tests(const std::string &dir) {
   return 0;
 }
 
+static bool same(const ccgpu_counters &a, const ccgpu_counters &b) {
+  return a.frames == b.frames && a.frame_errors == b.frame_errors && a.bit_errors == b.bit_errors &&
+         a.iterations == b.iterations && a.failures == b.failures && a.undetected == b.undetected;
+}
+
+// device groups: the same objects created under a cc::device_group shard every point over the members and must
+// return the counters of the one-device run (the noise is keyed by the global frame index).  `devices` may name
+// one device several times (then the sharding / merging is exercised on a single GPU).
+static int group_tests(const std::string &dir, const std::vector<int> &devices) {
+  using nms = normalized_min_sum_tag<50, std::ratio<8, 10> >;
+  using nmsq = fixed_normalized_min_sum_tag<50, std::ratio<8, 10> >;
+  device_group::use(std::vector<int>());
+  decoder s_nms = primitive_bch<6, errors<5>, nms>(), s_q = primitive_bch<6, errors<5>, nmsq>(),
+          s_bm = primitive_bch<6, errors<5>, berlekamp_massey_tag>(), s_big = primitive_bch<8, errors<18>, nms>(),
+          s_ms31 = primitive_bch<5, dmin<7>, min_sum_tag<50> >(), s_un = uncoded(100);
+  device_group::use(devices);
+  CHECK(device_group::current() && device_group::current()->size() == static_cast<int>(devices.size()));
+  decoder g_nms = primitive_bch<6, errors<5>, nms>(), g_q = primitive_bch<6, errors<5>, nmsq>(),
+          g_bm = primitive_bch<6, errors<5>, berlekamp_massey_tag>(), g_big = primitive_bch<8, errors<18>, nms>(),
+          g_ms31 = primitive_bch<5, dmin<7>, min_sum_tag<50> >(), g_un = uncoded(100);
+  CHECK(g_q.to_string() == "(63, 36, 11)-NMSQ");
+  const uint64_t sizes[] = { 1, 7, 16384, 100003, 1000000 };
+  for (uint64_t frames : sizes) {
+    CHECK(same(s_nms.awgn_point(4.0, frames, 3, 5, 77), g_nms.awgn_point(4.0, frames, 3, 5, 77)));
+    CHECK(same(s_q.awgn_point(4.0, frames, 3, 5, 77), g_q.awgn_point(4.0, frames, 3, 5, 77)));
+    CHECK(same(s_bm.awgn_point(5.0, frames, 3, 5, 77), g_bm.awgn_point(5.0, frames, 3, 5, 77)));
+    CHECK(same(s_un.awgn_point(5.0, frames, 3, 5, 77), g_un.awgn_point(5.0, frames, 3, 5, 77)));
+  }
+  CHECK(same(s_big.awgn_point(6.0, 50001, 1, 2), g_big.awgn_point(6.0, 50001, 1, 2)));
+  for (unsigned w = 0; w <= 4; ++w) CHECK(same(s_ms31.bitflip_point(w), g_ms31.bitflip_point(w)));
+  // batched decode with host buffers, sharded: identical outputs
+  {
+    device_group::use(std::vector<int>());
+    primitive_bch<6, errors<5>, nms> one;
+    device_group::use(devices);
+    primitive_bch<6, errors<5>, nms> many;
+    const unsigned n = 63, frames = 70001;
+    std::vector<float> y(size_t(frames) * n);
+    uint64_t lcg = 99;
+    for (auto &v : y) {
+      lcg = lcg * 6364136223846793005ull + 1442695040888963407ull;
+      v = 1.0f + 1.6f * (float((lcg >> 40) & 0xffff) / 65536.0f - 0.5f) * 1.7f;
+    }
+    std::vector<uint8_t> b1(y.size()), f1(frames), i1(frames), b2(y.size()), f2(frames), i2(frames);
+    one.correct_batch(y.data(), frames, b1.data(), f1.data(), i1.data());
+    many.correct_batch(y.data(), frames, b2.data(), f2.data(), i2.data());
+    CHECK(b1 == b2 && f1 == f2 && i1 == i2);
+  }
+  // the whole sweep: byte-identical log
+  {
+    const std::string d1 = dir + "/one", dn = dir + "/group";
+    CHECK(::mkdir(d1.c_str(), 0755) == 0 && ::mkdir(dn.c_str(), 0755) == 0);
+    awgn_simulation(s_nms, 0.5, 0).samples_cap(300000).output_dir(d1)();
+    awgn_simulation(g_nms, 0.5, 0).samples_cap(300000).output_dir(dn)();
+    std::ifstream a(d1 + "/(63, 36, 11)-NMS.log"), b(dn + "/(63, 36, 11)-NMS.log");
+    std::stringstream sa, sb;
+    sa << a.rdbuf();
+    sb << b.rdbuf();
+    CHECK(!sa.str().empty() && sa.str() == sb.str());
+  }
+  device_group::use(std::vector<int>());
+  std::cout << "group tests ok (" << devices.size() << " members)" << std::endl;
+  return 0;
+}
+
 int main(int argc, char **argv) {
   if (argc >= 2 && std::string(argv[1]) == "--host") return host_tests();
+  if (argc >= 4 && std::string(argv[1]) == "--group") {  // --group <scratch dir> <device> [<device> ...]
+    std::vector<int> devices;
+    for (int i = 3; i < argc; ++i) devices.push_back(std::atoi(argv[i]));
+    return group_tests(argv[2], devices);
+  }
   if (argc >= 3 && std::string(argv[1]) == "--gpu") return gpu_tests(argv[2]);
   std::cerr << "usage: host_layer_test --host | --gpu <scratch dir>" << std::endl;
   return 2;

@@ -125,3 +125,47 @@ def test_bitflips_program(bins, tmp_path, kat):
         for w in range(4):
             row = kat["bitflip_31_16_7"][str(w)]
             assert abs(float(lines[1 + w].split()[1]) - row[tag] / row["patterns"]) < 1e-12, (tag, w)
+
+
+@pytest.mark.gpu
+def test_device_group_on_one_gpu(bins, tmp_path):
+    """ccgpu_group / cc::device_group with three members that all sit on device 0: sharding by global frame index and
+    the in-library counter merge give exactly the one-device counters, outputs and sweep log"""
+    r = subprocess.run([bins["host_layer_test"], "--group", str(tmp_path), "0", "0", "0"], capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_device_group_on_all_gpus(bins, tmp_path):
+    """the same on every GPU of the box (1 vs N devices give identical counters through the C++ layer)"""
+    import torch
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("one GPU only")
+    r = subprocess.run([bins["host_layer_test"], "--group", str(tmp_path)] + [str(i) for i in range(n)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_cli_gpus_device_and_stop_rule(bins, tmp_path):
+    """--gpus N shards every point over N devices and must not change a byte of the log; --device picks the first
+    device; --stop-rule gf2 changes the decoders' stop test (benchmark.cc used to parse and drop both)"""
+    import torch
+    n = min(2, torch.cuda.device_count())
+    common = ["--k", "5", "--dmin", "7", "--algorithm", "nms", "--max-samples", "200000", "--seed", "5"]
+    logs = {}
+    for tag, extra in (("one", []), ("gpus", ["--gpus", str(max(n, 1)), "--device", "0"]), ("gf2", ["--stop-rule", "gf2"])):
+        d = tmp_path / tag
+        d.mkdir()
+        r = subprocess.run([bins["benchmark"]] + common + extra + ["--out", str(d)], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        logs[tag] = open(d / "(31, 16, 7)-NMS.log").read()
+    assert logs["one"] == logs["gpus"]
+    assert logs["one"] != logs["gf2"]   # the GF(2) syndrome accepts non-zero codewords: different WER / iteration statistics
+    r = subprocess.run([bins["benchmark"]] + common + ["--device", "99", "--out", str(tmp_path)], capture_output=True, text=True,
+                       timeout=120)
+    assert r.returncode != 0 or "ccgpu_create failed" in (r.stdout + r.stderr)
+    r = subprocess.run([bins["benchmark"]] + common + ["--stop-rule", "bogus"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0

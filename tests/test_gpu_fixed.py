@@ -126,12 +126,19 @@ def test_fixed_redundant_rows(ctx, catalogue):
 def test_fixed_bound_is_enforced(ctx, catalogue):
     """parameter sets whose column sums could leave the exactly representable range are rejected, not mis-decoded"""
     import channelcoding_b200 as cc
-    code = make_code(ctx, catalogue["bch_63_36"])  # column weight 18
+    code = make_code(ctx, catalogue["bch_63_36"])
     y = np.ones((4, 63), np.float32)
+    wcol = int(code.H().sum(axis=0).max())  # 12 for the 27-row H(), 18 for the redundant 63-row matrix
+    bad = (2048 - 31) // wcol + 1
     with pytest.raises(cc.CcgpuError) as ei:
-        code.decode(y, "MS_Q", quant=(8.0, 31, 127))  # 18 * 127 + 31 > 2048
-    assert ei.value.code == cc._lib.ERR_UNSUPPORTED
-    code.decode(y, "NMS_Q", 0.8, quant=(8.0, 31, 127))  # fn_h(127) = 102: 18 * 102 + 31 = 1867 fits
+        code.decode(y, "MS_Q", quant=(8.0, 31, bad))
+    assert ei.value.code == cc._lib.ERR_UNSUPPORTED and "2048" in str(ei.value)
+    code.decode(y, "MS_Q", quant=(8.0, 31, bad - 1))
+    code.decode(y, "NMS_Q", 0.8, quant=(8.0, 31, bad))  # fn_h(bad) = rne(0.8 bad) fits
+    code.set_rows(63)
+    with pytest.raises(cc.CcgpuError):
+        code.decode(y, "MS_Q", quant=(8.0, 31, bad - 1))  # column weight 18 now
+    code.set_rows(27)
     with pytest.raises(cc.CcgpuError):
         code.decode(y, "NMS_Q", 1.5)
     g = ctx.from_dense(code.H()[np.random.default_rng(0).permutation(27)], 36 / 63)  # general H: CSR kernel, float only
@@ -209,3 +216,56 @@ def test_fixed_mbbp(ctx, catalogue):
     # decode_mbbp has no quant argument: the defaults are the plain call's defaults
     b, L, it, f, ch = code.decode_mbbp(y, [0], "NMS_Q", 0.8)
     assert np.array_equal(b, plain[0]) and np.array_equal(it, plain[2]) and np.array_equal(f, plain[3])
+
+
+@pytest.mark.parametrize("name,ebno", [("bch_15_7", 6.0), ("bch_31_16", 6.5), ("bch_63_36", 7.0), ("bch_127_64", 8.0),
+                                       ("bch_255_131", 9.0)])
+def test_fixed_all_positive_shortcut_is_exact(ctx, name, ebno, catalogue):
+    """fresh frames whose QUANTISED channel values are all positive are retired inside the refill loop (no iteration
+    executed) when the totals are not requested: identical bits / iteration index / failure flag / counters to the full
+    path (CCGPU_QUICK=0, and L requested) and to the restatement; zeros after quantisation, NaNs and ties never take
+    the shortcut wrongly"""
+    import os
+    e = catalogue[name]
+    code = make_code(ctx, e)
+    n = e["n"]
+    rng = np.random.default_rng(zlib.crc32(("quickq" + name).encode()))
+    frames = 6001 if n < 255 else 1501
+    y = (1 + oracle.sigma(e["rate"], ebno) * rng.standard_normal((frames, n))).astype(np.float32)
+    y[0] = 1.0
+    y[1, 3] = 0.05           # positive, but quantises to 0 at scale 8
+    y[2] = np.inf
+    y[3, 5] = np.nan         # quantises to 0
+    y[4] = 0.0625            # tie 0.5 -> 0
+    y[5, n - 1] = -0.0
+    q = QUANT[name][0]
+    yi = np.clip(np.rint(np.nan_to_num(y * np.float32(q[0]), nan=0.0)), -q[1], q[1])
+    allpos = (yi > 0).all(axis=1)
+    assert 0.15 < allpos.mean() < 0.98
+    for variant, alpha, beta, mi, stop in (("MS_Q", 1, 0, 50, 0), ("NMS_Q", 0.8, 0, 50, 1), ("OMS_Q", 1, 0.3, 20, 0),
+                                           ("NMS_Q", 0.8, 0, 1, 0), ("MS_Q", 1, 0, 5, 2)):
+        full = code.decode(y, variant, alpha, beta, mi, stop, want_L=True, quant=q)
+        try:
+            os.environ["CCGPU_QUICK"] = "1"
+            fast = code.decode(y, variant, alpha, beta, mi, stop, want_L=False, quant=q)
+            os.environ["CCGPU_QUICK"] = "0"
+            slow = code.decode(y, variant, alpha, beta, mi, stop, want_L=False, quant=q)
+        finally:
+            del os.environ["CCGPU_QUICK"]
+        what = "%s %s stop=%d" % (name, variant, stop)
+        for other in (fast, slow):
+            assert np.array_equal(other[0], full[0]) and np.array_equal(other[2], full[2]) and np.array_equal(other[3], full[3]), what
+        if stop != 2:
+            assert not fast[0][allpos].any() and not fast[2][allpos].any() and not fast[3][allpos].any(), what
+    hi = 1500 if n < 255 else 60
+    ref = oracle.min_sum_fixed(code.H(), y[:hi], "NMS_Q", 0.8, 0.0, 50, 0, *q)
+    os.environ["CCGPU_QUICK"] = "1"
+    try:
+        fast = code.decode(y[:hi], "NMS_Q", 0.8, 0.0, 50, 0, want_L=False, quant=q)
+        c1 = code.awgn_point(ebno, 300001 if n < 255 else 60001, "NMS_Q", 0.8, seed=3, point=1, quant=q)
+        os.environ["CCGPU_QUICK"] = "0"
+        c0 = code.awgn_point(ebno, 300001 if n < 255 else 60001, "NMS_Q", 0.8, seed=3, point=1, quant=q)
+    finally:
+        del os.environ["CCGPU_QUICK"]
+    assert np.array_equal(fast[0], ref[0]) and np.array_equal(fast[2].astype(np.uint32), ref[2]) and np.array_equal(fast[3], ref[3])
+    assert c0 == c1

@@ -6,8 +6,10 @@
 //
 //   g++ -std=c++17 -O2 -Iinclude tools/benchmark.cc -Lchannelcoding_b200 -lccgpu -Wl,-rpath,... -pthread
 //
-// Additions: --seed is honoured (the reference parses and drops it), --stop-rule ref|gf2,
-// --max-samples N, --errors W (bit-flip weight, bitflips.c++ uses 6), --out DIR, --device D.
+// Additions: --seed is honoured (the reference parses and drops it), --stop-rule ref|gf2 (stop test of the soft
+// decoders: the reference's integer zero-overlap rule or the GF(2) syndrome), --max-samples N, --errors W (bit-flip
+// weight, bitflips.c++ uses 6), --out DIR, --device D (first CUDA device), --gpus N (shard every point over N devices
+// D .. D+N-1 through a ccgpu_group; the counters, hence the logs, are identical to the one-GPU run).
 #include <getopt.h>
 
 #include <cmath>
@@ -45,7 +47,7 @@ template <unsigned Q> static void add_power(std::vector<decoder> &v) {
                "--k <5|6|7|all>   code length n = 2^k - 1   (repeatable)\n"
                "--dmin <3|5|7|9|all>                          (repeatable)\n"
                "--seed <num>  --seed-time  --threads <num>\n"
-               "--stop-rule <ref|gf2>  --max-samples <num>  --errors <num>  --out <dir>  --device <num>\n";
+               "--stop-rule <ref|gf2>  --max-samples <num>  --errors <num>  --out <dir>  --device <num>  --gpus <num>\n";
   std::exit(EXIT_FAILURE);
 }
 
@@ -59,7 +61,7 @@ int main(int argc, char *const argv[]) {
   std::set<unsigned> ks, dmins;
   std::string simulation = "awgn", out = ".";
   uint64_t seed = 0, max_samples = 1000000;
-  size_t threads = 1, errors = 6;  // one GPU is shared: sweeps are serialised unless asked otherwise
+  size_t threads = 1, errors = 6;  // the GPUs are shared: sweeps are serialised unless asked otherwise
   static struct option options[] = {
     { "simulation", required_argument, nullptr, 'i' }, { "algorithm", required_argument, nullptr, 'a' },
     { "k", required_argument, nullptr, 'k' },          { "dmin", required_argument, nullptr, 'd' },
@@ -67,9 +69,11 @@ int main(int argc, char *const argv[]) {
     { "threads", required_argument, nullptr, 'm' },    { "max-samples", required_argument, nullptr, 'x' },
     { "errors", required_argument, nullptr, 'e' },     { "out", required_argument, nullptr, 'o' },
     { "stop-rule", required_argument, nullptr, 'r' },  { "device", required_argument, nullptr, 'g' },
+    { "gpus", required_argument, nullptr, 'n' },
     { nullptr, 0, nullptr, 0 },
   };
   std::string stop = "ref";
+  int device = 0, gpus = 1;
   for (;;) {
     int idx = 0;
     const int c = getopt_long_only(argc, argv, "", options, &idx);
@@ -86,12 +90,19 @@ int main(int argc, char *const argv[]) {
     case 'e': errors = std::stoull(optarg); break;
     case 'o': out = optarg; break;
     case 'r': stop = lower(optarg); break;
-    case 'g': break;
+    case 'g': device = std::stoi(optarg); break;
+    case 'n': gpus = std::stoi(optarg); break;
     default: usage();
     }
   }
   if (simulation != "awgn" && simulation != "bitflip") usage();
+  if (stop != "ref" && stop != "gf2") usage();
+  if (gpus < 1 || device < 0) usage();
   if (algorithms.count("all")) algorithms.clear();
+  // the flags act on the decoders at construction: stop rule, first device, number of devices per point
+  set_default_stop_rule(stop == "gf2" ? stop_rule::gf2_parity : stop_rule::reference);
+  set_default_device(device);
+  device_group::use(gpus, device);
 
   std::vector<decoder> decoders;
   add_power<5>(decoders);
@@ -116,7 +127,6 @@ int main(int argc, char *const argv[]) {
     std::cout << "The selection is empty" << std::endl;
     usage();
   }
-  (void)stop;  // the stop rule is a property of the code object; the catalogue uses the reference's rule
   thread_pool p(threads);
   for (const decoder *d : chosen) {
     if (simulation == "awgn")
