@@ -55,6 +55,8 @@ def lib():
     L.ccgpu_destroy.restype = None
     L.ccgpu_last_error.argtypes = [vp]
     L.ccgpu_last_error.restype = C.c_char_p
+    L.ccgpu_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.ccgpu_build_info.restype = C.c_char_p
     L.ccgpu_set_stream.argtypes = [vp, vp]
     L.ccgpu_get_stream.argtypes = [vp]
     L.ccgpu_get_stream.restype = vp
@@ -79,6 +81,8 @@ def lib():
     L.ccgpu_sigma.restype = dbl
     L.ccgpu_shannon_limit_db.argtypes = [dbl]
     L.ccgpu_shannon_limit_db.restype = dbl
+    L.ccgpu_shannon_limit_db_numeric.argtypes = [dbl]
+    L.ccgpu_shannon_limit_db_numeric.restype = dbl
     L.ccgpu_sweep_start_ebno.argtypes = [dbl, dbl]
     L.ccgpu_sweep_start_ebno.restype = dbl
     L.ccgpu_sweep_samples.argtypes = [dbl, u64]
@@ -118,11 +122,11 @@ def lib():
 
 
 # every symbol include/ccgpu.h declares (tests check that the library exports all of them)
-EXPORTS = ["ccgpu_abi_version", "ccgpu_create", "ccgpu_destroy", "ccgpu_last_error", "ccgpu_set_stream",
+EXPORTS = ["ccgpu_abi_version", "ccgpu_create", "ccgpu_destroy", "ccgpu_last_error", "ccgpu_set_option", "ccgpu_build_info", "ccgpu_set_stream",
            "ccgpu_get_stream", "ccgpu_sync", "ccgpu_kernel_launches", "ccgpu_bch_create", "ccgpu_rs_create",
            "ccgpu_code_from_dense", "ccgpu_code_set_rows", "ccgpu_code_destroy", "ccgpu_code_get_info",
            "ccgpu_code_to_string", "ccgpu_code_H", "ccgpu_code_H_alt", "ccgpu_code_poly", "ccgpu_gf_tables", "ccgpu_encode",
-           "ccgpu_decode_llr", "ccgpu_sigma", "ccgpu_shannon_limit_db", "ccgpu_sweep_start_ebno", "ccgpu_sweep_samples", "ccgpu_awgn_llr", "ccgpu_awgn_point", "ccgpu_awgn_point_hard", "ccgpu_bitflip_point",
+           "ccgpu_decode_llr", "ccgpu_sigma", "ccgpu_shannon_limit_db", "ccgpu_shannon_limit_db_numeric", "ccgpu_sweep_start_ebno", "ccgpu_sweep_samples", "ccgpu_awgn_llr", "ccgpu_awgn_point", "ccgpu_awgn_point_hard", "ccgpu_bitflip_point",
            "ccgpu_gf_decode", "ccgpu_gf_decode_erasures", "ccgpu_code_set_recheck", "ccgpu_decode_llr_mbbp", "ccgpu_awgn_point_uncoded", "ccgpu_gf_decode_erasures_pgz",
            "ccgpu_awgn_point_mbbp", "ccgpu_group_create", "ccgpu_group_destroy", "ccgpu_group_size", "ccgpu_group_ctx",
            "ccgpu_group_last_error", "ccgpu_group_set_min_frames", "ccgpu_group_awgn_point", "ccgpu_group_awgn_point_hard",

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -31,8 +32,13 @@ struct ccgpu_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   std::mutex mu;
+  std::mutex err_mu;   // guards err: entry-point checks fail before `mu` is taken, and pool threads share a context
   std::string err;
-  uint64_t launches = 0;
+  std::atomic<uint64_t> launches{0};
+  // overrides (ccgpu_set_option; the environment variables CCGPU_QUICK / CCGPU_WORK_BATCH give the initial values and
+  // are read ONCE, at ccgpu_create)
+  int opt_quick = -1;        // -1: the host's estimate decides (api.cu ccgpu_awgn_point), 0 / 1: force
+  int opt_work_batch = 0;    // 0: default
   // device staging for host-pointer calls (grown on demand)
   void *d_stage = nullptr;
   size_t d_stage_bytes = 0;
@@ -66,7 +72,10 @@ struct ccgpu_code {
 namespace {
 
 int fail(ccgpu_ctx *ctx, int code, const std::string &msg) {
-  if (ctx) ctx->err = msg;
+  if (ctx) {
+    std::lock_guard<std::mutex> g(ctx->err_mu);
+    ctx->err = msg;
+  }
   return code;
 }
 int cuda_fail(ccgpu_ctx *ctx, cudaError_t e, const char *what) {
@@ -549,7 +558,7 @@ int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsP
   // the fixed-point kernels test for all-positive frames at run time when the hint is set; with several frames per
   // warp all of them must be all-positive at once, which is rare: measured slower there (profiles/r2_notes.md)
   if (vn == VN_FIX && c->cyc[VN_FIX] && !c->cyc[VN_FIX]->cta && c->cyc[VN_FIX]->fpw != 1) mp.quick_hint = 0;
-  if (const char *env = std::getenv("CCGPU_QUICK")) mp.quick_hint = std::atoi(env) != 0;
+  if (ctx->opt_quick >= 0) mp.quick_hint = ctx->opt_quick;
   const int vq = (mp.quick_hint && vn != VN_SPA && vn != VN_FIX && mp.L == nullptr && p->stop_rule != CCGPU_STOP_NONE && c->cyc[vn + VN_QUICK] &&
                   c->cyc[vn] && c->cyc[vn + VN_QUICK]->k == c->cyc[vn]->k && c->cyc[vn + VN_QUICK]->fpw == 1)
                      ? vn + VN_QUICK
@@ -568,7 +577,7 @@ int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsP
       while ((uint64_t(1) << shift) < 4 * warps) ++shift;
       mp.work_batch = 32;
       mp.work_shift = shift;
-      if (const char *env = std::getenv("CCGPU_WORK_BATCH")) mp.work_batch = std::max(1, std::atoi(env));
+      if (ctx->opt_work_batch > 0) mp.work_batch = static_cast<unsigned>(ctx->opt_work_batch);
     }
     void *args[] = { &mp };
     CU(cudaLaunchKernel(reinterpret_cast<const void *>(e->fn), dim3(grid), dim3(e->threads), args, c->smem[vq], stream));
@@ -677,6 +686,8 @@ int ccgpu_create(int device, ccgpu_ctx **out) {
     delete ctx;
     return CCGPU_ERR_CUDA;
   }
+  if (const char *env = std::getenv("CCGPU_QUICK")) ctx->opt_quick = std::atoi(env) != 0;
+  if (const char *env = std::getenv("CCGPU_WORK_BATCH")) ctx->opt_work_batch = std::max(1, std::atoi(env));
   *out = ctx;
   return CCGPU_OK;
 }
@@ -702,7 +713,33 @@ void ccgpu_destroy(ccgpu_ctx *ctx) {
   delete ctx;
 }
 
-const char *ccgpu_last_error(const ccgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : "no context"; }
+const char *ccgpu_last_error(const ccgpu_ctx *ctx) {
+  // a copy per calling thread: the context's string may be rewritten by another pool thread at any time
+  thread_local std::string copy;
+  if (!ctx) return "no context";
+  {
+    std::lock_guard<std::mutex> g(const_cast<ccgpu_ctx *>(ctx)->err_mu);
+    copy = ctx->err;
+  }
+  return copy.c_str();
+}
+
+int ccgpu_set_option(ccgpu_ctx *ctx, const char *name, int64_t value) {
+  if (!ctx || !name) return CCGPU_ERR_INVALID;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  const std::string n(name);
+  if (n == "quick") ctx->opt_quick = value < 0 ? -1 : (value ? 1 : 0);
+  else if (n == "work_batch") ctx->opt_work_batch = value > 0 ? static_cast<int>(std::min<int64_t>(value, 1024)) : 0;
+  else return fail(ctx, CCGPU_ERR_INVALID, "unknown option " + n);
+  return CCGPU_OK;
+}
+
+const char *ccgpu_build_info(void) {
+#define CCGPU_STR_(x) #x
+#define CCGPU_STR(x) CCGPU_STR_(x)
+  return "nvcc " CCGPU_STR(__CUDACC_VER_MAJOR__) "." CCGPU_STR(__CUDACC_VER_MINOR__) "." CCGPU_STR(__CUDACC_VER_BUILD__)
+         " sm_100a abi " CCGPU_STR(CCGPU_ABI_VERSION);
+}
 
 int ccgpu_set_stream(ccgpu_ctx *ctx, void *cuda_stream) {
   if (!ctx) return CCGPU_ERR_INVALID;
@@ -722,7 +759,7 @@ int ccgpu_sync(ccgpu_ctx *ctx) {
   CU(cudaStreamSynchronize(ctx->stream));
   return CCGPU_OK;
 }
-uint64_t ccgpu_kernel_launches(const ccgpu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+uint64_t ccgpu_kernel_launches(const ccgpu_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 
 // ---- codes -------------------------------------------------------------------------------------
 static int make_code(ccgpu_ctx *ctx, CodeSpec &&spec, ccgpu_code **out) {
@@ -914,9 +951,49 @@ static double biawgn_capacity(double snr) {  // bit/use at Es/N0 = snr (linear);
   return 1.0 - acc;
 }
 
+// The reference's table of the Shannon limit Eb/N0 [dB] of the binary-input AWGN channel (simulation.c++:21-52): 131
+// (rate, limit) pairs, rates 0.01 .. 0.80 in steps of 0.01, then an irregular grid up to 0.999.  The sweep start of
+// every decoder -- hence the points of every log file -- derives from these very numbers, so they are reproduced as
+// data, not recomputed (a numerically computed limit is 2.419 dB at rate 0.8387 where the table's rounded-up entry is
+// 2.503 dB: BCH(31,26) then starts at 3.0 instead of 3.5 dB).
+static const double kShannonRates[131] = {
+  0.01,  0.02,  0.03,  0.04,  0.05,  0.06,  0.07,  0.08,  0.09,  0.10,  0.11,  0.12,  0.13,  0.14,  0.15,  0.16,  0.17,
+  0.18,  0.19,  0.20,  0.21,  0.22,  0.23,  0.24,  0.25,  0.26,  0.27,  0.28,  0.29,  0.30,  0.31,  0.32,  0.33,  0.34,
+  0.35,  0.36,  0.37,  0.38,  0.39,  0.40,  0.41,  0.42,  0.43,  0.44,  0.45,  0.46,  0.47,  0.48,  0.49,  0.50,  0.51,
+  0.52,  0.53,  0.54,  0.55,  0.56,  0.57,  0.58,  0.59,  0.60,  0.61,  0.62,  0.63,  0.64,  0.65,  0.66,  0.67,  0.68,
+  0.69,  0.70,  0.71,  0.72,  0.73,  0.74,  0.75,  0.76,  0.77,  0.78,  0.79,  0.800, 0.807, 0.817, 0.827, 0.837, 0.846,
+  0.855, 0.864, 0.872, 0.880, 0.887, 0.894, 0.900, 0.907, 0.913, 0.918, 0.924, 0.929, 0.934, 0.938, 0.943, 0.947, 0.951,
+  0.954, 0.958, 0.961, 0.964, 0.967, 0.970, 0.972, 0.974, 0.976, 0.978, 0.980, 0.982, 0.983, 0.984, 0.985, 0.986, 0.987,
+  0.988, 0.989, 0.990, 0.991, 0.992, 0.993, 0.994, 0.995, 0.996, 0.997, 0.998, 0.999 };
+static const double kShannonLimits[131] = {
+  -1.548, -1.531, -1.500, -1.470, -1.440, -1.409, -1.378, -1.347, -1.316, -1.285, -1.254, -1.222, -1.190, -1.158, -1.126,
+  -1.094, -1.061, -1.028, -0.995, -0.963, -0.928, -0.896, -0.861, -0.827, -0.793, -0.757, -0.724, -0.687, -0.651, -0.616,
+  -0.579, -0.544, -0.507, -0.469, -0.432, -0.394, -0.355, -0.314, -0.276, -0.236, -0.198, -0.156, -0.118, -0.074, -0.032,
+  0.010,  0.055,  0.097,  0.144,  0.188,  0.233,  0.279,  0.326,  0.374,  0.424,  0.474,  0.526,  0.574,  0.628,  0.682,
+  0.734,  0.791,  0.844,  0.904,  0.960,  1.021,  1.084,  1.143,  1.208,  1.275,  1.343,  1.412,  1.483,  1.554,  1.628,
+  1.708,  1.784,  1.867,  1.952,  2.045,  2.108,  2.204,  2.302,  2.402,  2.503,  2.600,  2.712,  2.812,  2.913,  3.009,
+  3.114,  3.205,  3.312,  3.414,  3.500,  3.612,  3.709,  3.815,  3.906,  4.014,  4.115,  4.218,  4.304,  4.425,  4.521,
+  4.618,  4.725,  4.841,  4.922,  5.004,  5.104,  5.196,  5.307,  5.418,  5.484,  5.549,  5.615,  5.681,  5.756,  5.842,
+  5.927,  6.023,  6.119,  6.234,  6.360,  6.495,  6.651,  6.837,  7.072,  7.378,  7.864 };
+
+// ebno(rate) of simulation.c++:56-70: rate <= 0.8 indexes the table with size_t(rate * 100) (that is the entry of the
+// next tabulated rate, the table starts at 0.01), rate >= 0.999 takes the last entry, anything between the first
+// tabulated rate >= rate from index 80 on.  Rates outside (0, 1] have no entry in the reference (it would throw /
+// read out of range): the first / last entry is returned.
 double ccgpu_shannon_limit_db(double rate) {
+  if (!(rate > 0.0)) return kShannonLimits[0];
+  if (rate <= 0.800) return kShannonLimits[static_cast<size_t>(rate * 100)];
+  if (rate >= 0.999) return kShannonLimits[130];
+  size_t i = 80;
+  while (i < 130 && !(kShannonRates[i] >= rate)) ++i;
+  return kShannonLimits[i];
+}
+
+// the same limit computed from the channel capacity (numerical integral + bisection); not used by the sweep, kept as
+// a cross-check of the table (tests/test_host_abi.py) and for callers who want the exact figure of an arbitrary rate
+double ccgpu_shannon_limit_db_numeric(double rate) {
   if (!(rate > 0.0)) return -1.59;
-  const double r = rate <= 0.8 ? (std::floor(rate * 100) + 1) / 100.0 : std::min(rate, 0.999);
+  const double r = std::min(rate, 0.9995);
   double lo = -3.0, hi = 12.0;
   for (int i = 0; i < 60; ++i) {
     const double mid = 0.5 * (lo + hi);

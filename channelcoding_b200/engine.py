@@ -97,6 +97,20 @@ class Context:
         import torch
         self.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def set_option(self, name, value):
+        """tuning overrides (ccgpu_set_option): "quick" -1 / 0 / 1, "work_batch" n"""
+        self._check(_lib.lib().ccgpu_set_option(self._h, name.encode(), int(value)))
+
+    def _follow_torch(self, *tensors):
+        """Work on torch tensors must be ordered with torch's own work on them (allocation, fills, frees): run on
+        torch's CURRENT stream of this device.  The context's private stream is non-blocking, so it orders with
+        nothing torch does; a zero-fill issued by torch could land after the kernel's atomics."""
+        if any(t is not None and _is_torch(t) for t in tensors):
+            import torch
+            cur = torch.cuda.current_stream(self.device).cuda_stream
+            if _lib.lib().ccgpu_get_stream(self._h) != cur:
+                self.set_stream(cur)
+
     def sync(self):
         self._check(_lib.lib().ccgpu_sync(self._h))
 
@@ -137,6 +151,7 @@ class Context:
     def awgn_llr(self, n, sigma, seed, point, frame0, frames, out=None):
         if out is None:
             out = np.empty((frames, n), np.float32)
+        self._follow_torch(out)
         self._check(_lib.lib().ccgpu_awgn_llr(self._h, n, float(sigma), seed, point, frame0, frames, _ptr(out)))
         return out
 
@@ -225,6 +240,7 @@ class Code:
                 failed = np.empty(frames, np.uint8)
             else:
                 bits, L, it, failed = out
+        self.ctx._follow_torch(y, bits)
         self.ctx._check(_lib.lib().ccgpu_decode_llr(self.ctx._h, self._h, C.byref(p), _ptr(y), frames, _ptr(bits),
                                                     _ptr(L), _ptr(it), _ptr(failed)))
         return bits, L, it, failed
@@ -235,6 +251,7 @@ class Code:
         out: optional torch uint64/int64 CUDA tensor of 8 slots that is accumulated into (no sync)."""
         p = ms_params(variant, alpha, beta, max_iter, stop_rule, quant)
         if out is not None:
+            self.ctx._follow_torch(out)
             self.ctx._check(_lib.lib().ccgpu_awgn_point(self.ctx._h, self._h, C.byref(p), float(ebno_db), seed, point,
                                                         frame0, frames, _ptr(out)))
             return out
@@ -262,6 +279,7 @@ class Code:
             bits, it, failed, chosen = (np.empty((frames, self.n), np.uint8), np.empty(frames, np.uint8),
                                         np.empty(frames, np.uint8), np.empty(frames, np.uint8))
             L = np.empty((frames, self.n), np.float32) if want_L else None
+        self.ctx._follow_torch(y)
         self.ctx._check(_lib.lib().ccgpu_decode_llr_mbbp(self.ctx._h, self._h, C.byref(p), sh.ctypes.data, len(sh), _ptr(y),
                                                          frames, _ptr(bits), _ptr(L), _ptr(it), _ptr(failed), _ptr(chosen)))
         return bits, L, it, failed, chosen
@@ -313,6 +331,7 @@ class Code:
             if out is None:
                 out = (np.empty_like(words), np.empty(cnt, np.uint8), np.empty(cnt, np.uint8))
         corrected, nerr, failed = out
+        self.ctx._follow_torch(words, corrected)
         if erasures is None:
             self.ctx._check(_lib.lib().ccgpu_gf_decode(self.ctx._h, self._h, _ptr(words), cnt, _ptr(corrected),
                                                        _ptr(nerr), _ptr(failed)))

@@ -126,6 +126,7 @@ int ccgpu_abi_version(void);
 /* device: CUDA ordinal.  Replaces nothing in the reference (it has no device). */
 int ccgpu_create(int device, ccgpu_ctx **out);
 void ccgpu_destroy(ccgpu_ctx *ctx);
+/* text of the context's last error; the pointer stays valid until the calling thread's next call of this function */
 const char *ccgpu_last_error(const ccgpu_ctx *ctx);
 /* use an existing cudaStream_t (e.g. torch's current stream) instead of the context's own */
 int ccgpu_set_stream(ccgpu_ctx *ctx, void *cuda_stream);
@@ -133,6 +134,15 @@ void *ccgpu_get_stream(ccgpu_ctx *ctx);
 int ccgpu_sync(ccgpu_ctx *ctx);
 /* number of engine kernels launched through this context so far */
 uint64_t ccgpu_kernel_launches(const ccgpu_ctx *ctx);
+/* tuning overrides.  "quick": -1 the library decides per call whether frames with all-positive channel values are
+ * retired without iterating (same results either way), 0 / 1 force it off / on -- the parity tests drive both paths
+ * with it; "work_batch": most frame indices a warp takes from the frame queue per atomic (0 = default).  The
+ * environment variables CCGPU_QUICK / CCGPU_WORK_BATCH are read once, at ccgpu_create, as initial values. */
+int ccgpu_set_option(ccgpu_ctx *ctx, const char *name, int64_t value);
+/* "nvcc <version> sm_100a abi <n>": the toolkit the kernels were compiled with.  The bit-exactness of the ordered
+ * column sums rests on properties of the generated code that tests/test_gpu_parity.py re-validates for every
+ * compiled shape; a different toolkit must pass them again. */
+const char *ccgpu_build_info(void);
 
 /* ---- codes ---------------------------------------------------------------------------------------
  * cyclic::primitive_bch<q, Capability>() -- codes/bch.h:16-161 on top of codes/cyclic.h:67-386.
@@ -185,10 +195,13 @@ int ccgpu_decode_llr(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_para
 
 /* sigma of simulation.c++:83-85: 1 / sqrt(2 * rate * 10^(ebno_db/10)) */
 double ccgpu_sigma(double rate, double ebno_db);
-/* Shannon limit Eb/N0 [dB] of the binary-input AWGN channel at `rate`: replaces the lookup ebno(rate)
- * of simulation.c++:56-70 in the tables :21-52.  Like that lookup, rates <= 0.8 are first rounded up
- * to the next multiple of 0.01.  Computed (numerical capacity integral + bisection), not tabulated. */
+/* Shannon limit Eb/N0 [dB] of the binary-input AWGN channel at `rate` exactly as the reference looks it up: ebno(rate)
+ * of simulation.c++:56-70 over its 131-entry table :21-52 (reproduced as data: the first point of every sweep, hence
+ * every log file, derives from these numbers).  Pinned on 2028 rates dumped from the reference (tests/golden/shannon.json). */
 double ccgpu_shannon_limit_db(double rate);
+/* the same limit computed from the capacity of the channel (integral + bisection); a cross-check of the table and the
+ * exact figure for rates between its entries.  Not used by the sweep. */
+double ccgpu_shannon_limit_db_numeric(double rate);
 /* first Eb/N0 point of a sweep, simulation.c++:105-107: (size_t(limit / step) + 1 / step) * step,
  * a negative limit counting as 0 */
 double ccgpu_sweep_start_ebno(double rate, double step);

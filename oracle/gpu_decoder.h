@@ -12,7 +12,7 @@
 #include <ccgpu.h>
 #include "codes/bch.h"
 
-template <typename Code, int Variant /* CCGPU_MS .. CCGPU_NMS2D */>
+template <typename Code, int Variant /* CCGPU_MS .. CCGPU_OMS_Q */>
 class gpu_decoder {
   Code code;                                    // the reference's own object: g, h, H(), rate, to_string
   std::shared_ptr<ccgpu_ctx> ctx;
@@ -34,7 +34,13 @@ public:
     dev.reset(d, ccgpu_code_destroy);
     params = ccgpu_ms_params{ Variant, CCGPU_STOP_REF_ZERO_OVERLAP, iterations, 0, alpha, beta };
   }
-  std::string to_string() const { return code.to_string(); }
+  // "(n, l, dmin)-TAG" (cyclic.h:282-287) with the tag of the VARIANT this decoder runs, not of the Code's algebraic
+  // default: the string is the log-file name (simulation.c++:98), two variants of one code must not collide
+  std::string to_string() const {
+    static const char *const tags[] = { "MS", "NMS", "OMS", "SCMS1", "SCMS2", "2DNMS", "SPA", "MSQ", "NMSQ", "OMSQ" };
+    const std::string s = code.to_string();
+    return s.substr(0, s.find_last_of('-') + 1) + tags[Variant];
+  }
   template <typename R> std::vector<R> correct(const std::vector<float> &b) const {
     std::vector<uint8_t> bits(n);
     uint8_t failed = 0;

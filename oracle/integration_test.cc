@@ -16,10 +16,10 @@ int main(int argc, char **argv) {
   // the reference's type-erased decoder holding the GPU adapter (simulation.h:58-60)
   decoder ms = gpu_decoder<cyclic::primitive_bch<5, dmin<7> >, CCGPU_MS>();
   decoder nms = gpu_decoder<cyclic::primitive_bch<6, errors<5> >, CCGPU_NMS>(0.8);
-  if (ms.to_string() != "(31, 16, 7)-PGZ" || nms.n() != 63) return 3;  // to_string comes from the reference object
+  if (ms.to_string() != "(31, 16, 7)-MS" || nms.to_string() != "(63, 36, 11)-NMS" || nms.n() != 63) return 3;  // code part from the reference object, tag from the variant
   // the reference's own exhaustive bit-flip loop (simulation.c++:156-213) calling correct() per pattern
   bitflip_simulation(ms, 3)();
-  std::ifstream f("(31, 16, 7)-PGZ.log");
+  std::ifstream f("(31, 16, 7)-MS.log");
   std::stringstream ss;
   ss << f.rdbuf();
   std::cout << ss.str();

@@ -55,9 +55,11 @@ static int host_tests() {
   CHECK(awgn_simulation::start_ebno(7.0 / 15, 0.5) == 1.0);
   CHECK(awgn_simulation::start_ebno(64.0 / 127, 0.5) == 1.0);
   CHECK(awgn_simulation::start_ebno(131.0 / 255, 0.5) == 1.0);
-  CHECK(std::fabs(ccgpu_shannon_limit_db(0.495) - 0.188) < 0.003);  // table: rate 0.50 -> 0.188 dB
-  CHECK(std::fabs(ccgpu_shannon_limit_db(0.795) - 2.045) < 0.01);   // table: rate 0.80 -> 2.045 dB
-  CHECK(std::fabs(ccgpu_shannon_limit_db(0.005) - (-1.548)) < 0.02); // table: rate 0.01 -> -1.548 dB
+  CHECK(ccgpu_shannon_limit_db(0.495) == 0.188);   // table: rates (0.49, 0.50] -> 0.188 dB
+  CHECK(ccgpu_shannon_limit_db(0.795) == 2.045);   // table: rate 0.80 -> 2.045 dB
+  CHECK(ccgpu_shannon_limit_db(0.005) == -1.548);  // table: rate 0.01 -> -1.548 dB
+  CHECK(ccgpu_shannon_limit_db(26.0 / 31) == 2.503 && awgn_simulation::start_ebno(26.0 / 31, 0.5) == 3.5);  // BCH(31,26)
+  CHECK(std::fabs(ccgpu_shannon_limit_db_numeric(0.5) - 0.188) < 0.003);
   std::cout << "host tests ok" << std::endl;
   return 0;
 }

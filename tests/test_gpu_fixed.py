@@ -223,7 +223,7 @@ def test_fixed_mbbp(ctx, catalogue):
 def test_fixed_all_positive_shortcut_is_exact(ctx, name, ebno, catalogue):
     """fresh frames whose QUANTISED channel values are all positive are retired inside the refill loop (no iteration
     executed) when the totals are not requested: identical bits / iteration index / failure flag / counters to the full
-    path (CCGPU_QUICK=0, and L requested) and to the restatement; zeros after quantisation, NaNs and ties never take
+    path (option quick = 0, and L requested) and to the restatement; zeros after quantisation, NaNs and ties never take
     the shortcut wrongly"""
     import os
     e = catalogue[name]
@@ -246,12 +246,12 @@ def test_fixed_all_positive_shortcut_is_exact(ctx, name, ebno, catalogue):
                                            ("NMS_Q", 0.8, 0, 1, 0), ("MS_Q", 1, 0, 5, 2)):
         full = code.decode(y, variant, alpha, beta, mi, stop, want_L=True, quant=q)
         try:
-            os.environ["CCGPU_QUICK"] = "1"
+            ctx.set_option("quick", 1)
             fast = code.decode(y, variant, alpha, beta, mi, stop, want_L=False, quant=q)
-            os.environ["CCGPU_QUICK"] = "0"
+            ctx.set_option("quick", 0)
             slow = code.decode(y, variant, alpha, beta, mi, stop, want_L=False, quant=q)
         finally:
-            del os.environ["CCGPU_QUICK"]
+            ctx.set_option("quick", -1)
         what = "%s %s stop=%d" % (name, variant, stop)
         for other in (fast, slow):
             assert np.array_equal(other[0], full[0]) and np.array_equal(other[2], full[2]) and np.array_equal(other[3], full[3]), what
@@ -259,13 +259,13 @@ def test_fixed_all_positive_shortcut_is_exact(ctx, name, ebno, catalogue):
             assert not fast[0][allpos].any() and not fast[2][allpos].any() and not fast[3][allpos].any(), what
     hi = 1500 if n < 255 else 60
     ref = oracle.min_sum_fixed(code.H(), y[:hi], "NMS_Q", 0.8, 0.0, 50, 0, *q)
-    os.environ["CCGPU_QUICK"] = "1"
+    ctx.set_option("quick", 1)
     try:
         fast = code.decode(y[:hi], "NMS_Q", 0.8, 0.0, 50, 0, want_L=False, quant=q)
         c1 = code.awgn_point(ebno, 300001 if n < 255 else 60001, "NMS_Q", 0.8, seed=3, point=1, quant=q)
-        os.environ["CCGPU_QUICK"] = "0"
+        ctx.set_option("quick", 0)
         c0 = code.awgn_point(ebno, 300001 if n < 255 else 60001, "NMS_Q", 0.8, seed=3, point=1, quant=q)
     finally:
-        del os.environ["CCGPU_QUICK"]
+        ctx.set_option("quick", -1)
     assert np.array_equal(fast[0], ref[0]) and np.array_equal(fast[2].astype(np.uint32), ref[2]) and np.array_equal(fast[3], ref[3])
     assert c0 == c1

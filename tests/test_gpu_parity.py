@@ -644,11 +644,11 @@ def test_all_positive_shortcut_is_exact(ctx, name, ebno, catalogue):
                                            ("SCMS1", 1, 0, 30, 1), ("SCMS2", 1, 0, 50, 0), ("2DNMS", 0.9, 0.8, 25, 1),
                                            ("NMS", 0.8, 0, 1, 0), ("MS", 1, 0, 5, 2)):
         full = code.decode(y, variant, alpha, beta, mi, stop, want_L=True)
-        os.environ["CCGPU_QUICK"] = "1"   # the QUICK instantiation (normally chosen by ccgpu_awgn_point at high Eb/N0)
+        ctx.set_option("quick", 1)   # the QUICK instantiation (normally chosen by ccgpu_awgn_point at high Eb/N0)
         try:
             fast = code.decode(y, variant, alpha, beta, mi, stop, want_L=False)
         finally:
-            del os.environ["CCGPU_QUICK"]
+            ctx.set_option("quick", -1)
         assert fast[1] is None
         what = "%s %s stop=%d" % (name, variant, stop)
         assert np.array_equal(fast[0], full[0]) and np.array_equal(fast[2], full[2]) and np.array_equal(fast[3], full[3]), what
@@ -657,13 +657,37 @@ def test_all_positive_shortcut_is_exact(ctx, name, ebno, catalogue):
             assert not fast[0][ok].any() and not fast[2][ok].any() and not fast[3][ok].any(), what
     hi = 1500 if n < 255 else 60
     ob, _, oi, of = oracle.min_sum(code.H(), y[6:hi], "NMS", 0.8, 0.0, 50, 0)   # (the rows with inf / nan left out)
-    os.environ["CCGPU_QUICK"] = "1"
+    ctx.set_option("quick", 1)
     try:
         fast = code.decode(y[6:hi], "NMS", 0.8, 0.0, 50, 0, want_L=False)
         c1 = code.awgn_point(ebno, 300000 if n < 255 else 60000, "NMS", 0.8, seed=3, point=1)
-        os.environ["CCGPU_QUICK"] = "0"
+        ctx.set_option("quick", 0)
         c0 = code.awgn_point(ebno, 300000 if n < 255 else 60000, "NMS", 0.8, seed=3, point=1)
     finally:
-        del os.environ["CCGPU_QUICK"]
+        ctx.set_option("quick", -1)
     assert np.array_equal(fast[0], ob) and np.array_equal(fast[2].astype(np.uint32), oi) and np.array_equal(fast[3], of)
     assert c0 == c1   # fused Monte-Carlo point: identical counters with and without the shortcut
+
+
+def test_every_compiled_shape_keeps_the_reference_order(ctx, catalogue):
+    """Guard for the ordered column sums (ms_cyclic.cuh VOLCS: program order through volatile shared-memory accesses
+    instead of one __syncwarp per tap -- formally a race under independent thread scheduling, in practice decided by
+    the SASS ptxas emits).  EVERY catalogue code (each has its own compiled shape) x every flavour: the totals L must
+    carry the reference's float32 bit patterns, i.e. the rows were added in ascending order.  The toolkit is pinned
+    by tests/test_host_abi.py::test_build_info; a new nvcc has to pass this test before it ships."""
+    rng = np.random.default_rng(2024)
+    seen = 0
+    for name, e in sorted(catalogue.items()):
+        if e["family"] != 0:
+            continue
+        code = make_code(ctx, e)
+        assert code.kernel == 1, name
+        H = code.H()
+        frames = 96 if e["n"] <= 63 else (24 if e["n"] <= 127 else 8)
+        y = (1 + oracle.sigma(e["rate"], 3.0) * rng.standard_normal((frames, e["n"]))).astype(np.float32)
+        for variant, alpha, beta in (("MS", 1, 0), ("NMS", 0.8, 0), ("OMS", 1, 0.05), ("SCMS1", 1, 0), ("SCMS2", 1, 0),
+                                     ("2DNMS", 0.9, 0.8)):
+            assert_same(code.decode(y, variant, alpha, beta, 12, 0), oracle.min_sum(H, y, variant, alpha, beta, 12, 0),
+                        "%s %s" % (name, variant))
+        seen += 1
+    assert seen >= 16

@@ -111,3 +111,45 @@ def test_no_packed_fma_in_library():
     sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True, check=True).stdout
     assert "FFMA2" not in sass and "FMUL2" not in sass
     assert "FADD2" in sass  # the packed variable-node adds of ms_cyclic.cuh
+
+
+def test_shannon_table_matches_reference(catalogue):
+    """ccgpu_shannon_limit_db / ccgpu_sweep_start_ebno against values dumped from the reference's own ebno()
+    (simulation.c++:21-70, :105-106; generator oracle/make_golden_shannon.py): every catalogue rate and a grid of 2005
+    rates, steps 0.5 and 0.1, exact equality"""
+    import json
+    L = _lib.lib()
+    with open(os.path.join(ROOT, "tests", "golden", "shannon.json")) as f:
+        g = json.load(f)
+    assert set(g["catalogue"]) == set(catalogue)
+    rows = list(g["catalogue"].values()) + g["grid"]
+    assert len(rows) > 2000
+    for row in rows:
+        assert L.ccgpu_shannon_limit_db(row["rate"]) == row["limit"], row
+        for step in (0.5, 0.1):
+            key = "start_%g" % step
+            if key in row:
+                assert L.ccgpu_sweep_start_ebno(row["rate"], step) == row[key], row
+    # the rate the round-1 review caught: BCH(31,26) starts at 3.5 dB, not 3.0
+    assert L.ccgpu_sweep_start_ebno(26 / 31, 0.5) == 3.5
+    # the numerically computed limit agrees with the table at the tabulated rates (cross-check of the data)
+    for rate, limit in ((0.10, -1.285), (0.50, 0.188), (0.80, 2.045), (0.9, 3.205), (0.99, 6.023)):
+        assert abs(L.ccgpu_shannon_limit_db_numeric(rate) - limit) < 0.02, rate
+
+
+def test_build_info():
+    """the toolkit the shipped kernels were compiled with is pinned: the ordered column sums of ms_cyclic.cuh rely on
+    code-generation properties that tests/test_gpu_parity.py::test_every_compiled_shape_keeps_the_reference_order
+    validates for THIS nvcc"""
+    L = _lib.lib()
+    info = L.ccgpu_build_info().decode()
+    assert info.startswith("nvcc 12.9.") and "sm_100a" in info and info.endswith("abi 2"), info
+
+
+def test_last_error_is_per_thread_copy():
+    """ccgpu_last_error hands out a copy owned by the calling thread (another pool thread may overwrite the context's
+    string at any time); without a device the only reachable texts are the null-context ones"""
+    L = _lib.lib()
+    assert L.ccgpu_last_error(None) == b"no context"
+    assert L.ccgpu_group_last_error(None) == b"no group"
+    assert L.ccgpu_set_option(None, b"quick", 1) == _lib.ERR_INVALID
