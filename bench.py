@@ -225,8 +225,9 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("CCGPU_NCCL_DEBUG", "WARN")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL logs to stdout by default: keep stdout to the one JSON line
+        # NCCL logs to stdout by default: route it to stderr so that stdout stays the one JSON line; the log LEVEL
+        # (NCCL_DEBUG) is left to the caller -- the driver counts the ranks from it
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():

@@ -431,7 +431,14 @@ void select_cyclic(ccgpu_code *c) {
     const bool exact = e->k == k && !e->wrap && c->shape.kind == 0;
     const bool redundant = e->k == 0 && e->wrap && k <= (e->cta ? e->threads : 32) * e->rpl;
     if (!exact && !redundant) continue;
-    if (c->cyc[e->vn] && !exact) continue;  // an exact shape wins over the redundant one
+    if (c->cyc[e->vn] && !exact) {
+      // an exact shape wins over a redundant one.  Between two redundant shapes the warp-per-frame one is kept for the
+      // float flavours (the CTA form pays a block barrier per tap and pass for the ordered column sum), but the
+      // fixed-point CTA kernel needs no such barriers and beats a warp kernel with three or more rows per lane
+      const MsCyclicEntry *old = c->cyc[e->vn];
+      const bool prefer_cta = e->vn == VN_FIX && e->cta && !old->cta && old->wrap && old->rpl >= 3;
+      if (!prefer_cta) continue;
+    }
     c->cyc[e->vn] = e;
   }
   for (int vn = 0; vn < VN_COUNT; ++vn) {

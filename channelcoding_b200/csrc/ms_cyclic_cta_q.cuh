@@ -20,7 +20,8 @@
 
 namespace ccgpu {
 
-template <class S> constexpr int ms_cta_q_min_blocks() { return S::RPL == 1 ? 4 : 2; }
+// packed messages per thread -> resident CTAs per SM the register allocation aims at
+template <class S> constexpr int ms_cta_q_min_blocks() { return S::RPL * S::W <= 32 ? 8 : S::RPL * S::W <= 72 ? 4 : 2; }
 
 template <class S>
 __global__ void __launch_bounds__(S::THREADS, ms_cta_q_min_blocks<S>()) ms_cyclic_cta_q_kernel(const __grid_constant__ MsParams p) {

@@ -346,6 +346,137 @@ class Code:
         return corrected, nerr, failed
 
 
+class Group:
+    """several GPUs of this host behind one handle (ccgpu_group): Monte-Carlo points are sharded over the member
+    devices by global frame index and the counters merged inside the library; `devices` may repeat an ordinal"""
+
+    def __init__(self, devices):
+        devices = list(range(devices)) if isinstance(devices, int) else list(devices)
+        arr = (C.c_int * len(devices))(*devices)
+        self._h = C.c_void_p()
+        rc = _lib.lib().ccgpu_group_create(len(devices), arr, C.byref(self._h))
+        if rc != 0:
+            raise CcgpuError(rc, "ccgpu_group_create(%s) failed -- not enough usable CUDA devices" % devices)
+        self.devices = devices
+        self.members = [_Member(self, m) for m in range(len(devices))]
+        self._codes = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            for gc in self._codes:  # the codes live on the members' contexts: release them first
+                for c in gc.codes:
+                    c.close()
+            for m in self.members:
+                m._h = None
+            _lib.lib().ccgpu_group_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CcgpuError(rc, _lib.lib().ccgpu_group_last_error(self._h).decode())
+
+    def set_min_frames(self, frames_per_member):
+        self._check(_lib.lib().ccgpu_group_set_min_frames(self._h, int(frames_per_member)))
+
+    def bch(self, q, errors=None, dmin=None):
+        return GroupCode(self, [m.bch(q, errors=errors, dmin=dmin) for m in self.members])
+
+    def rs(self, q, errors, mu=1, step=1):
+        return GroupCode(self, [m.rs(q, errors, mu, step) for m in self.members])
+
+
+class _Member(Context):
+    """a member context of a Group (owned by the group)"""
+
+    def __init__(self, group, member):
+        self._h = C.c_void_p(_lib.lib().ccgpu_group_ctx(group._h, member))
+        self.device = group.devices[member]
+        self._group = group
+
+    def close(self):
+        self._h = None
+
+
+class GroupCode:
+    """one code replicated on every member of a Group"""
+
+    def __init__(self, group, codes):
+        self.group, self.codes = group, codes
+        group._codes.append(self)
+        self._arr = (C.c_void_p * len(codes))(*[c._h for c in codes])
+        for k in ("n", "l", "k", "rate", "edges", "h_rows", "row_weight", "kernel"):
+            setattr(self, k, getattr(codes[0], k))
+
+    def to_string(self, tag):
+        return self.codes[0].to_string(tag)
+
+    def set_rows(self, rows):
+        for c in self.codes:
+            c.set_rows(rows)
+        self.h_rows, self.edges = self.codes[0].h_rows, self.codes[0].edges
+
+    def awgn_point(self, ebno_db, frames, variant="MS", alpha=1.0, beta=0.0, max_iter=50, stop_rule=STOP_REF_ZERO_OVERLAP,
+                   seed=0, point=0, frame0=0, quant=None):
+        p = ms_params(variant, alpha, beta, max_iter, stop_rule, quant)
+        c = Counters()
+        self.group._check(_lib.lib().ccgpu_group_awgn_point(self.group._h, self._arr, C.byref(p), float(ebno_db), seed, point,
+                                                            frame0, frames, C.addressof(c)))
+        return c.as_dict()
+
+    def awgn_point_hard(self, ebno_db, frames, seed=0, point=0, frame0=0):
+        c = Counters()
+        self.group._check(_lib.lib().ccgpu_group_awgn_point_hard(self.group._h, self._arr, float(ebno_db), seed, point, frame0,
+                                                                 frames, C.addressof(c)))
+        return c.as_dict()
+
+    def awgn_point_mbbp(self, ebno_db, frames, shifts, variant="MS", alpha=1.0, beta=0.0, max_iter=50,
+                        stop_rule=STOP_REF_ZERO_OVERLAP, seed=0, point=0, frame0=0):
+        p = ms_params(variant, alpha, beta, max_iter, stop_rule)
+        sh = np.ascontiguousarray(shifts, np.uint32)
+        c = Counters()
+        self.group._check(_lib.lib().ccgpu_group_awgn_point_mbbp(self.group._h, self._arr, C.byref(p), sh.ctypes.data, len(sh),
+                                                                 float(ebno_db), seed, point, frame0, frames, C.addressof(c)))
+        return c.as_dict()
+
+    def bitflip_point(self, weight, variant="MS", alpha=1.0, beta=0.0, max_iter=50, stop_rule=STOP_REF_ZERO_OVERLAP, first=0,
+                      count=0, quant=None):
+        p = ms_params(variant, alpha, beta, max_iter, stop_rule, quant)
+        c = Counters()
+        self.group._check(_lib.lib().ccgpu_group_bitflip_point(self.group._h, self._arr, C.byref(p), weight, first, count,
+                                                               C.addressof(c)))
+        return c.as_dict()
+
+    def decode(self, y, variant="MS", alpha=1.0, beta=0.0, max_iter=50, stop_rule=STOP_REF_ZERO_OVERLAP, want_L=True, out=None,
+               quant=None):
+        """ccgpu_group_decode_llr: host (numpy) buffers, frames sharded over the members"""
+        p = ms_params(variant, alpha, beta, max_iter, stop_rule, quant)
+        y = np.ascontiguousarray(y, np.float32).reshape(-1, self.n)
+        frames = y.shape[0]
+        if out is None:
+            out = (np.empty((frames, self.n), np.uint8), np.empty((frames, self.n), np.float32) if want_L else None,
+                   np.empty(frames, np.uint8), np.empty(frames, np.uint8))
+        bits, L, it, failed = out
+        self.group._check(_lib.lib().ccgpu_group_decode_llr(self.group._h, self._arr, C.byref(p), _ptr(y), frames, _ptr(bits),
+                                                            _ptr(L), _ptr(it), _ptr(failed)))
+        return bits, L, it, failed
+
+    def gf_decode(self, words, out=None):
+        words = np.ascontiguousarray(words, np.uint8).reshape(-1, self.n)
+        cnt = words.shape[0]
+        if out is None:
+            out = (np.empty_like(words), np.empty(cnt, np.uint8), np.empty(cnt, np.uint8))
+        corrected, nerr, failed = out
+        self.group._check(_lib.lib().ccgpu_group_gf_decode(self.group._h, self._arr, _ptr(words), cnt, _ptr(corrected),
+                                                           _ptr(nerr), _ptr(failed)))
+        return corrected, nerr, failed
+
+
 def sigma(rate, ebno_db):
     return _lib.lib().ccgpu_sigma(float(rate), float(ebno_db))
 

@@ -46,8 +46,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("CCGPU_NCCL_DEBUG", "WARN")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL logs to stdout by default: keep stdout to the one JSON line
+        # NCCL logs to stdout by default: route it to stderr so that stdout stays JSON lines; the log LEVEL is the caller's
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = cc.Context(local)
     ctx.use_torch_stream()
