@@ -115,10 +115,16 @@ int oracle_min_sum(const uint8_t *H, unsigned rows, unsigned cols, const float *
       for (unsigned col = 0; col < cols; col++)
         if (H[row * cols + col]) {
           if (variant == V_SPA) {
-            /* extension (unpinned): r = 2 atanh( prod_{i != col} tanh(q_i / 2) ) in float */
-            float prod = 1.0f;
-            for (unsigned i = 0; i < cols; i++)
-              if (i != col && H[row * cols + i]) prod *= tanhf(0.5f * q[row * cols + i]);
+            /* extension (unpinned): r = 2 atanh( prod_{i != col} tanh(q_i / 2) ) in float.  The exclusive product is
+             * associated like the device kernel's (ms_cyclic.cuh: prefix of the edges before col, in ascending column
+             * order, times the suffix accumulated from the last edge downwards), so that the only difference left
+             * between this restatement and the kernel is the last-ulp behaviour of tanhf / atanhf (libm vs CUDA). */
+            float prefix = 1.0f, suffix = 1.0f;
+            for (unsigned i = 0; i < col; i++)
+              if (H[row * cols + i]) prefix *= tanhf(0.5f * q[row * cols + i]);
+            for (unsigned i = cols; i-- > col + 1;)
+              if (H[row * cols + i]) suffix *= tanhf(0.5f * q[row * cols + i]);
+            float prod = prefix * suffix;
             /* clamp like the device kernel so that atanh stays finite */
             const float lim = 0.99999994f;
             if (prod > lim) prod = lim;
@@ -312,6 +318,89 @@ int oracle_min_sum_fixed_batch(const uint8_t *H, unsigned rows, unsigned cols, c
     unsigned it = 0;
     int rc = oracle_min_sum_fixed(H, rows, cols, y + f * cols, variant, alpha, beta, max_iter, stop_rule, q_scale,
                                   q_y_max, q_msg_max, bits + f * cols, L ? L + f * cols : 0, &it);
+    iter[f] = it;
+    failed[f] = (uint8_t)rc;
+  }
+  return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Sum-product in DOUBLE precision: the yardstick for the float32 sum-product kernel (extension, parity unpinned --
+ * the reference has no tanh-rule decoder).  Same flooding loop (soft_decision.h:161-202), same clamp of the exclusive
+ * product (the float32 constant 0.99999994), every operation in double.  L_out receives the totals of the last
+ * executed iteration as doubles. */
+int oracle_spa_f64(const uint8_t *H, unsigned rows, unsigned cols, const float *y, unsigned max_iter, int stop_rule,
+                   uint8_t *b_out, double *L_out, unsigned *iter_out) {
+  const size_t E = (size_t)rows * cols;
+  double *q = (double *)calloc(E, sizeof(double));
+  double *r = (double *)calloc(E, sizeof(double));
+  double *cs = (double *)calloc(cols, sizeof(double));
+  double *L = (double *)calloc(cols, sizeof(double));
+  uint8_t *b = (uint8_t *)calloc(cols, 1);
+  const double lim = (double)0.99999994f;
+  int rc = 1;
+  unsigned iteration;
+  for (iteration = 0; iteration < max_iter; iteration++) {
+    for (unsigned c = 0; c < cols; c++) cs[c] = 0.0;
+    for (unsigned row = 0; row < rows; row++)
+      for (unsigned col = 0; col < cols; col++)
+        if (H[row * cols + col]) cs[col] += r[row * cols + col];
+    for (unsigned row = 0; row < rows; row++)
+      for (unsigned col = 0; col < cols; col++)
+        if (H[row * cols + col]) q[row * cols + col] = (cs[col] - r[row * cols + col]) + (double)y[col];
+    for (unsigned row = 0; row < rows; row++)
+      for (unsigned col = 0; col < cols; col++)
+        if (H[row * cols + col]) {
+          double prod = 1.0;
+          for (unsigned i = 0; i < cols; i++)
+            if (i != col && H[row * cols + i]) prod *= tanh(0.5 * q[row * cols + i]);
+          if (prod > lim) prod = lim;
+          if (prod < -lim) prod = -lim;
+          r[row * cols + col] = 2.0 * atanh(prod);
+        }
+    for (unsigned c = 0; c < cols; c++) cs[c] = 0.0;
+    for (unsigned row = 0; row < rows; row++)
+      for (unsigned col = 0; col < cols; col++)
+        if (H[row * cols + col]) cs[col] += r[row * cols + col];
+    for (unsigned c = 0; c < cols; c++) {
+      L[c] = cs[c] + (double)y[c];
+      b[c] = (uint8_t)(L[c] < 0);
+    }
+    int stop = 0;
+    if (stop_rule == STOP_REF_ZERO_OVERLAP) {
+      stop = 1;
+      for (unsigned row = 0; row < rows && stop; row++) {
+        uint8_t acc = 0;
+        for (unsigned c = 0; c < cols; c++) acc = (uint8_t)(acc + H[row * cols + c] * b[c]);
+        if (acc) stop = 0;
+      }
+    } else if (stop_rule == STOP_GF2_PARITY) {
+      stop = 1;
+      for (unsigned row = 0; row < rows && stop; row++) {
+        unsigned acc = 0;
+        for (unsigned c = 0; c < cols; c++) acc ^= (unsigned)(H[row * cols + c] & b[c]);
+        if (acc) stop = 0;
+      }
+    } else {
+      stop = (iteration + 1 == max_iter);
+    }
+    if (stop) {
+      rc = 0;
+      break;
+    }
+  }
+  memcpy(b_out, b, cols);
+  if (L_out) memcpy(L_out, L, cols * sizeof(double));
+  *iter_out = iteration;
+  free(q); free(r); free(cs); free(L); free(b);
+  return rc;
+}
+
+int oracle_spa_f64_batch(const uint8_t *H, unsigned rows, unsigned cols, const float *y, uint64_t frames,
+                         unsigned max_iter, int stop_rule, uint8_t *bits, double *L, uint32_t *iter, uint8_t *failed) {
+  for (uint64_t f = 0; f < frames; f++) {
+    unsigned it = 0;
+    int rc = oracle_spa_f64(H, rows, cols, y + f * cols, max_iter, stop_rule, bits + f * cols, L ? L + f * cols : 0, &it);
     iter[f] = it;
     failed[f] = (uint8_t)rc;
   }

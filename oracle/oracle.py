@@ -45,6 +45,8 @@ def lib():
         L.oracle_min_sum_fixed_batch.argtypes = [_u8p, C.c_uint, C.c_uint, _f32p, C.c_uint64, C.c_int, C.c_double,
                                                  C.c_double, C.c_uint, C.c_int, C.c_float, C.c_int, C.c_int, _u8p,
                                                  C.c_void_p, _u32p, _u8p]
+        L.oracle_spa_f64_batch.argtypes = [_u8p, C.c_uint, C.c_uint, _f32p, C.c_uint64, C.c_uint, C.c_int, _u8p, C.c_void_p,
+                                           _u32p, _u8p]
         L.oracle_quantise.argtypes = [C.c_float, C.c_float, C.c_int]
         L.oracle_gf_tables.argtypes = [C.c_uint, C.c_uint, _u16p, _u16p]
         L.oracle_code_new.restype = C.c_void_p
@@ -76,6 +78,19 @@ def min_sum(H, y, variant="MS", alpha=1.0, beta=0.0, max_iter=50, stop_rule=STOP
     failed = np.zeros(f, np.uint8)
     lib().oracle_min_sum_batch(H, H.shape[0], H.shape[1], y, f, v, alpha, beta, max_iter, stop_rule,
                                bits, L.ctypes.data, it, failed)
+    return bits, L, it, failed
+
+
+def spa_f64(H, llr, max_iter=50, stop_rule=STOP_GF2_PARITY):
+    """sum-product in double precision (yardstick of the float32 SPA kernel) -> bits u8, L float64, iter u32, failed u8"""
+    H = np.ascontiguousarray(H, np.uint8)
+    y = np.ascontiguousarray(llr, np.float32).reshape(-1, H.shape[1])
+    f = y.shape[0]
+    bits = np.zeros((f, H.shape[1]), np.uint8)
+    L = np.zeros((f, H.shape[1]), np.float64)
+    it = np.zeros(f, np.uint32)
+    failed = np.zeros(f, np.uint8)
+    lib().oracle_spa_f64_batch(H, H.shape[0], H.shape[1], y, f, max_iter, stop_rule, bits, L.ctypes.data, it, failed)
     return bits, L, it, failed
 
 

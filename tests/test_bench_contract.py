@@ -34,11 +34,22 @@ def test_reference_arm_contract():
 @pytest.mark.gpu
 def test_gpu_arm_contract():
     d = run(["--steps", "3", "--warmup", "3", "--frames", "262144", "--e2e-frames", "65536", "--cpu-seconds", "1"])
-    assert BASE_KEYS | {"roofline", "gpu_launches", "clocks", "fused_monte_carlo", "alu", "smem"} <= set(d)
+    assert BASE_KEYS | {"roofline", "gpu_launches", "clocks", "fused_monte_carlo", "alu", "smem", "issue", "fixed_point"} <= set(d)
     assert d["gpu_launches"] == 3 and d["n_gpus"] == 1 and d["higher_is_better"] is True and d["vs_baseline"] is None
     assert d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"] < 1 and d["roofline"]["peak"] > 1000
     assert d["e2e"]["h2d_bytes_per_step"] == 65536 * 63 * 4 and d["e2e"]["value"] > 0
     assert d["cpu_baseline"]["value"] > 0 and d["value"] > 1000 * d["cpu_baseline"]["value"]
     assert abs(d["wer"] - 0.18) < 0.01 and abs(d["fused_monte_carlo"]["wer"] - 0.18) < 0.01
+    # round 2: the fixed-point decoder next to the headline, the host-side ceiling of the e2e path, and pipe counts that
+    # are withheld (null) unless the committed ncu capture is stamped with the hash of the sources in use
+    fx = d["fixed_point"]
+    assert fx["value"] > 1.3 * d["value"] and fx["speedup_edge_iterations"] > 1.4 and 0.15 < fx["wer"] < 0.23
+    assert 0 < d["e2e"]["frac_of_h2d_ceiling"] <= 1.05 and d["e2e"]["h2d_ceiling_gbs"] > 10
+    import bench
+    rec, current = bench.ncu_capture("K2 ms_cyclic BCH(63,36) NMS 4 dB resident")
+    if rec is not None and current:
+        assert 0 < d["smem"]["frac"] < 1 and 0 < d["issue"]["frac"] < 1 and d["roofline"]["traffic"] > 0
+    else:
+        assert d["smem"]["frac"] is None and d["issue"]["frac"] is None and d["roofline"]["traffic"] is None
     ref = run(["--impl", "reference", "--steps", "1", "--warmup", "0"])
     assert ref["config"]["workload"] == d["config"]["workload"] and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]

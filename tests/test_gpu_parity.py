@@ -140,40 +140,86 @@ def test_redundant_rows(ctx, name, rows, catalogue):
                     "redundant %s %d %s" % (name, rows, variant))
 
 
+SPA_TOL = 5e-2  # stated tolerance of the float32 sum-product totals: ||L - L64||_inf / ||L64||_inf per iteration (see below)
+
+
+def _first_divergence(code, H, llr, kmax):
+    """first iteration k at which the float32 kernel and the float64 yardstick decide a column differently ->
+    (k, column, |L64| there, ||L64||_inf) or None"""
+    for k in range(1, kmax + 1):
+        gb, gL, _, _ = code.decode(llr[None, :], "SPA", max_iter=k, stop_rule=2)
+        ob, oL, _, _ = oracle.spa_f64(H, llr[None, :], k, 2)
+        diff = np.nonzero(gb[0] != ob[0])[0]
+        if len(diff):
+            c = int(diff[0])
+            return k, c, abs(float(oL[0, c])), float(np.abs(oL[0]).max())
+    return None
+
+
 def test_sum_product_extension(ctx, catalogue):
-    """SPA (tanh rule) is not in the reference; float32 messages agree with the CPU restatement to
-    1e-3 relative on L and the hard decisions agree on >= 99.5 % of the frames (tanhf/atanhf differ
-    in the last ulp between libm and the GPU, and the exclusive product is associated differently)."""
+    """SPA (tanh rule) is an extension: the reference has no such decoder, so parity is UNPINNED by it.  The yardstick
+    is the same flooding loop in float64 (oracle_spa_f64).  north_star asks for "floating-point sum-product messages
+    agree within a stated relative tolerance"; stated and checked here:
+      * totals after k iterations (no stop rule): ||L_gpu - L64||_inf / ||L64||_inf <= 5e-2 for every frame and every
+        k tested, median below 5e-3.  The bound is that loose only because of SATURATED messages: the exclusive tanh
+        product is clamped to +-0.99999994, where one float32 ulp of the product moves 2 atanh by 0.35 -- on totals
+        of magnitude 20..70; unsaturated messages agree to 1e-6.
+      * BCH(15,7), 1..6 dB, 20 000 frames per point: hard decisions, iteration index and failure flag equal the
+        float64 run on >= 99.95 % of the frames, and EVERY disagreeing frame sits on a decision boundary: at the first
+        iteration where a decided bit differs, the float64 total of that column is inside the tolerance band.
+      * the float32 restatement (ms_oracle.c, same prefix x suffix association as the kernel) is compared as well."""
     e = catalogue["bch_15_7"]
     code = make_code(ctx, e)
+    H = code.H()
     rng = np.random.default_rng(4)
-    sig = oracle.sigma(e["rate"], 3.0)
-    y = (1 + sig * rng.standard_normal((2000, 15))).astype(np.float32)
-    llr = (2.0 / sig ** 2 * y).astype(np.float32)
-    gb, gL, gi, gf = code.decode(llr, "SPA", max_iter=10, stop_rule=1)
-    ob, oL, oi, of = oracle.min_sum(code.H(), llr, "SPA", max_iter=10, stop_rule=1)
-    same = (gi == oi) & (gf == of)
-    assert same.mean() >= 0.995
-    assert (gb[same] == ob[same]).all(axis=1).mean() >= 0.995
-    rel = np.abs(gL[same] - oL[same]) / np.maximum(1.0, np.abs(oL[same]))
-    assert np.median(rel) < 1e-5 and np.quantile(rel, 0.99) < 1e-3
+    total = agree = 0
+    for eb in (1.0, 2.0, 3.0, 4.0, 5.0, 6.0):
+        sig = oracle.sigma(e["rate"], eb)
+        llr = (2.0 / sig ** 2 * (1 + sig * rng.standard_normal((20000, 15)))).astype(np.float32)
+        gb, gL, gi, gf = code.decode(llr, "SPA", max_iter=50, stop_rule=1)
+        ob, oL, oi, of = oracle.spa_f64(H, llr, 50, 1)
+        same = (gi == oi) & (gf == of) & (gb == ob).all(axis=1)
+        total += len(same)
+        agree += int(same.sum())
+        for f in np.nonzero(~same)[0][:20]:
+            d = _first_divergence(code, H, llr[f], 50)
+            assert d is not None, (eb, f)
+            k, c, l64, linf = d
+            assert l64 <= SPA_TOL * linf, "frame %d at %g dB diverges at iteration %d away from a decision boundary: |L|=%g of %g" % (f, eb, k, l64, linf)
+        # per-iteration tolerance of the totals
+        for k in (1, 2, 3, 5, 10, 20):
+            _, La, _, _ = code.decode(llr[:3000], "SPA", max_iter=k, stop_rule=2)
+            _, Lb, _, _ = oracle.spa_f64(H, llr[:3000], k, 2)
+            rel = np.abs(La - Lb).max(axis=1) / np.abs(Lb).max(axis=1)
+            assert rel.max() <= SPA_TOL and np.median(rel) <= 5e-3, (eb, k, rel.max(), np.median(rel))
+        # float32 restatement vs the kernel: same association, only tanhf / atanhf differ in the last ulp
+        rb, rL, ri, rf = oracle.min_sum(H, llr[:5000], "SPA", max_iter=50, stop_rule=1)
+        same32 = (gi[:5000] == ri) & (gf[:5000] == rf) & (gb[:5000] == rb).all(axis=1)
+        assert same32.mean() >= 0.9995, (eb, same32.mean())
+    assert agree / total >= 0.9995, (agree, total)
     # the same on the general (CSR) kernel: rows permuted so that the cyclic structure is gone
+    sig = oracle.sigma(e["rate"], 3.0)
+    llr = (2.0 / sig ** 2 * (1 + sig * rng.standard_normal((4000, 15)))).astype(np.float32)
     perm = np.random.default_rng(2).permutation(code.h_rows)
-    g = ctx.from_dense(code.H()[perm], e["rate"])
+    g = ctx.from_dense(H[perm], e["rate"])
     assert code.kernel == 1 and g.kernel == 2
     gb2, gL2, gi2, gf2 = g.decode(llr, "SPA", max_iter=10, stop_rule=1)
-    ob2, oL2, oi2, of2 = oracle.min_sum(code.H()[perm], llr, "SPA", max_iter=10, stop_rule=1)
-    same2 = (gi2 == oi2) & (gf2 == of2)
-    assert same2.mean() >= 0.995 and (gb2[same2] == ob2[same2]).all(axis=1).mean() >= 0.995
-    # larger code on the cyclic kernel
+    ob2, oL2, oi2, of2 = oracle.spa_f64(H[perm], llr, 10, 1)
+    same2 = (gi2 == oi2) & (gf2 == of2) & (gb2 == ob2).all(axis=1)
+    assert same2.mean() >= 0.999
+    # larger code on the cyclic kernel: agreement and the same decision-boundary argument
     e63 = catalogue["bch_63_36"]
     c63 = make_code(ctx, e63)
+    H63 = c63.H()
     sig = oracle.sigma(e63["rate"], 4.0)
-    y = (2.0 / sig ** 2 * (1 + sig * rng.standard_normal((300, 63)))).astype(np.float32)
-    gb, gL, gi, gf = c63.decode(y, "SPA", max_iter=20, stop_rule=1)
-    ob, oL, oi, of = oracle.min_sum(c63.H(), y, "SPA", max_iter=20, stop_rule=1)
-    same = (gi == oi) & (gf == of)
-    assert same.mean() >= 0.97 and (gb[same] == ob[same]).all(axis=1).mean() >= 0.99
+    llr = (2.0 / sig ** 2 * (1 + sig * rng.standard_normal((400, 63)))).astype(np.float32)
+    gb, gL, gi, gf = c63.decode(llr, "SPA", max_iter=20, stop_rule=1)
+    ob, oL, oi, of = oracle.spa_f64(H63, llr, 20, 1)
+    same = (gi == oi) & (gf == of) & (gb == ob).all(axis=1)
+    assert same.mean() >= 0.98, same.mean()
+    for f in np.nonzero(~same)[0][:8]:
+        d = _first_divergence(c63, H63, llr[f], 20)
+        assert d is not None and d[2] <= SPA_TOL * d[3], (f, d)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -189,6 +235,52 @@ def test_channel_kernel(ctx):
     a = ctx.awgn_llr(63, 0.7, 1, 0, 0, 1000)
     b = ctx.awgn_llr(63, 0.7, 1, 0, 500, 500)
     assert np.array_equal(a[500:], b)
+
+
+def test_channel_distribution(ctx):
+    """the GPU channel kernel itself (Philox4x32-10 + MUFU Box-Muller), not its closeness to the CPU restatement:
+    1.0e8 samples against the standard normal distribution -- four moments, the Kolmogorov-Smirnov distance on a
+    4000-bin grid, tail probabilities and the lag-1 correlation, each within a 4-sigma band of its sampling error"""
+    import math
+    import torch
+    n, frames, sigma_f = 63, 1600000, 0.75
+    y = torch.empty((frames, n), dtype=torch.float32, device="cuda")
+    ctx.awgn_llr(n, sigma_f, seed=11, point=5, frame0=10 ** 12, frames=frames, out=y)
+    ctx.sync()
+    z = ((y.double() - 1.0) / float(np.float32(sigma_f))).flatten()
+    N = z.numel()
+    assert N >= 10 ** 8
+    m = z.mean().item()
+    c = z - m
+    var = (c * c).mean().item()
+    skew = (c ** 3).mean().item() / var ** 1.5
+    kurt = (c ** 4).mean().item() / var ** 2 - 3.0
+    assert abs(m) < 4 / math.sqrt(N), m
+    assert abs(var - 1.0) < 4 * math.sqrt(2.0 / N), var
+    assert abs(skew) < 4 * math.sqrt(6.0 / N), skew
+    assert abs(kurt) < 4 * math.sqrt(24.0 / N), kurt
+    # Kolmogorov-Smirnov on a grid: sup |F_N - Phi| over 4000 bin edges in [-8, 8]; the 99.9 % critical value is 1.95 / sqrt(N)
+    bins = 4000
+    hist = torch.histc(z.float(), bins=bins, min=-8.0, max=8.0).double()
+    below = (z < -8.0).sum().item()
+    cdf = (torch.cumsum(hist, 0) + below) / N
+    edges = torch.linspace(-8.0, 8.0, bins + 1, dtype=torch.float64, device="cuda")[1:]
+    phi = 0.5 * (1.0 + torch.erf(edges / math.sqrt(2.0)))
+    ks = (cdf - phi).abs().max().item()
+    assert ks < 1.95 / math.sqrt(N) + 2e-6, ks  # (+ float32 binning of the grid)
+    # tails (what the word error rate at high Eb/N0 lives on)
+    for thr in (2.0, 3.0, 4.0, 4.5):
+        p = 0.5 * math.erfc(thr / math.sqrt(2.0))
+        for tail in ((z > thr), (z < -thr)):
+            k = tail.sum().item()
+            assert abs(k - N * p) < 4.5 * math.sqrt(N * p) + 1, (thr, k, N * p)
+    # neighbouring samples (same Philox block / Box-Muller pair and across blocks) are uncorrelated
+    zz = z.view(frames, n)
+    for lag in (1, 2, 4):
+        r = (zz[:, :-lag] * zz[:, lag:]).mean().item()
+        assert abs(r) < 4.5 / math.sqrt(frames * (n - lag)), (lag, r)
+    r = (zz[:-1, :] * zz[1:, :]).mean().item()   # same column of consecutive frames
+    assert abs(r) < 4.5 / math.sqrt((frames - 1) * n), r
 
 
 def test_fused_point_equals_streaming(ctx, catalogue):
@@ -312,6 +404,33 @@ def test_wer_matches_reference_statistics(ctx, catalogue):
         p1, p2 = rw / rf, c["frame_errors"] / c["frames"]
         se = math.sqrt(p1 * (1 - p1) / rf + p2 * (1 - p2) / c["frames"])
         assert abs(p1 - p2) <= 1.96 * se + 1e-9, (eb, p1, p2, se)
+
+
+def test_wer_matches_reference_at_1e5_frames(ctx, catalogue):
+    """the statistical leg with power: nine points (BCH(15,7) MS, BCH(63,36) NMS, BCH(127,64) NMS, three Eb/N0 each)
+    for which the REFERENCE ITSELF simulated 1e5 frames with its own noise source (oracle/make_golden_wer.py ->
+    tests/golden/ref_wer.json).  The engine simulates 1e7 frames per point (its own sampling error is a tenth of the
+    reference's), so the comparison is against the binomial interval of the reference's finite sample:
+    every point inside 3.3 sigma (99.9 %: nine comparisons at 95 % would fail a correct engine every third run),
+    at least seven of the nine inside the 95 % interval, and no systematic bias (mean signed deviation small).
+    A relative WER bias of 2 % in the channel kernel is 2.6 sigma at the WER = 0.64 point and would show."""
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_wer.json")) as f:
+        gold = json.load(f)
+    assert len(gold["points"]) == 9 and all(p["frames"] >= 100000 for p in gold["points"])
+    devs = []
+    for i, p in enumerate(gold["points"]):
+        e = catalogue[p["code"]]
+        code = make_code(ctx, e)
+        frames = 10_000_000 if e["n"] <= 63 else 4_000_000
+        c = code.awgn_point(p["ebno_db"], frames, p["variant"], p["alpha"], 0.0, p["max_iter"], seed=77, point=i)
+        pr, pg = p["word_errors"] / p["frames"], c["frame_errors"] / c["frames"]
+        se = math.sqrt(pg * (1 - pg) / p["frames"] + pg * (1 - pg) / frames)
+        devs.append((pr - pg) / se)
+        assert abs(devs[-1]) <= 3.3, (p["code"], p["ebno_db"], pr, pg, devs[-1])
+    devs = np.array(devs)
+    assert (np.abs(devs) <= 1.96).sum() >= 7, devs
+    assert abs(devs.mean()) <= 1.2, devs   # nine independent unit normals: the mean has sigma 1/3
 
 
 # ---------------------------------------------------------------------------------------------------
