@@ -77,6 +77,7 @@ def lib():
     L.ccgpu_gf_tables.argtypes = [u32, u32, vp, vp]
     L.ccgpu_encode.argtypes = [vp, u8p, u64, u8p]
     L.ccgpu_decode_llr.argtypes = [vp, vp, C.POINTER(MsParams), vp, u64, vp, vp, vp, vp]
+    L.ccgpu_decode_llr_packed.argtypes = [vp, vp, C.POINTER(MsParams), vp, u64, vp, vp]
     L.ccgpu_sigma.argtypes = [dbl, dbl]
     L.ccgpu_sigma.restype = dbl
     L.ccgpu_shannon_limit_db.argtypes = [dbl]
@@ -126,7 +127,7 @@ EXPORTS = ["ccgpu_abi_version", "ccgpu_create", "ccgpu_destroy", "ccgpu_last_err
            "ccgpu_get_stream", "ccgpu_sync", "ccgpu_kernel_launches", "ccgpu_bch_create", "ccgpu_rs_create",
            "ccgpu_code_from_dense", "ccgpu_code_set_rows", "ccgpu_code_destroy", "ccgpu_code_get_info",
            "ccgpu_code_to_string", "ccgpu_code_H", "ccgpu_code_H_alt", "ccgpu_code_poly", "ccgpu_gf_tables", "ccgpu_encode",
-           "ccgpu_decode_llr", "ccgpu_sigma", "ccgpu_shannon_limit_db", "ccgpu_shannon_limit_db_numeric", "ccgpu_sweep_start_ebno", "ccgpu_sweep_samples", "ccgpu_awgn_llr", "ccgpu_awgn_point", "ccgpu_awgn_point_hard", "ccgpu_bitflip_point",
+           "ccgpu_decode_llr", "ccgpu_decode_llr_packed", "ccgpu_sigma", "ccgpu_shannon_limit_db", "ccgpu_shannon_limit_db_numeric", "ccgpu_sweep_start_ebno", "ccgpu_sweep_samples", "ccgpu_awgn_llr", "ccgpu_awgn_point", "ccgpu_awgn_point_hard", "ccgpu_bitflip_point",
            "ccgpu_gf_decode", "ccgpu_gf_decode_erasures", "ccgpu_code_set_recheck", "ccgpu_decode_llr_mbbp", "ccgpu_awgn_point_uncoded", "ccgpu_gf_decode_erasures_pgz",
            "ccgpu_awgn_point_mbbp", "ccgpu_group_create", "ccgpu_group_destroy", "ccgpu_group_size", "ccgpu_group_ctx",
            "ccgpu_group_last_error", "ccgpu_group_set_min_frames", "ccgpu_group_awgn_point", "ccgpu_group_awgn_point_hard",

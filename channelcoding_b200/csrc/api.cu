@@ -432,18 +432,21 @@ void select_cyclic(ccgpu_code *c) {
     const bool redundant = e->k == 0 && e->wrap && k <= (e->cta ? e->threads : 32) * e->rpl;
     if (!exact && !redundant) continue;
     if (c->cyc[e->vn] && !exact) {
-      // an exact shape wins over a redundant one.  Between two redundant shapes the warp-per-frame one is kept for the
-      // float flavours (the CTA form pays a block barrier per tap and pass for the ordered column sum), but the
-      // fixed-point CTA kernel needs no such barriers and beats a warp kernel with three or more rows per lane
+      // an exact shape wins over a redundant one.  Between two redundant shapes the CTA form beats a warp kernel with
+      // three or more rows per lane (255 registers, spills) when its column sum needs no block barrier per tap: the
+      // fixed-point kernel (no order to keep) and the float kernel in gather form (dyn_smem > 0, ms_cyclic_cta.cuh)
       const MsCyclicEntry *old = c->cyc[e->vn];
-      const bool prefer_cta = e->vn == VN_FIX && e->cta && !old->cta && old->wrap && old->rpl >= 3;
+      const bool prefer_cta = (e->vn == VN_FIX || e->dyn_smem > 0) && e->cta && !old->cta && old->wrap && old->rpl >= 3;
       if (!prefer_cta) continue;
     }
     c->cyc[e->vn] = e;
   }
   for (int vn = 0; vn < VN_COUNT; ++vn) {
     if (!c->cyc[vn]) continue;
-    c->smem[vn] = c->cyc[vn]->cta ? 0 : size_t(kMsThreads / 32) * 2 * 32 * c->cyc[vn]->np * sizeof(float);
+    c->smem[vn] = c->cyc[vn]->cta ? size_t(c->cyc[vn]->dyn_smem) : size_t(kMsThreads / 32) * 2 * 32 * c->cyc[vn]->np * sizeof(float);
+    if (c->smem[vn] > 48 * 1024)
+      cudaFuncSetAttribute(reinterpret_cast<const void *>(c->cyc[vn]->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           static_cast<int>(c->smem[vn]));
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void *>(c->cyc[vn]->fn),
                                                   c->cyc[vn]->threads, c->smem[vn]);
@@ -567,7 +570,7 @@ int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsP
   if (vn == VN_FIX && c->cyc[VN_FIX] && !c->cyc[VN_FIX]->cta && c->cyc[VN_FIX]->fpw != 1) mp.quick_hint = 0;
   if (ctx->opt_quick >= 0) mp.quick_hint = ctx->opt_quick;
   const int vq = (mp.quick_hint && vn != VN_SPA && vn != VN_FIX && mp.L == nullptr && p->stop_rule != CCGPU_STOP_NONE && c->cyc[vn + VN_QUICK] &&
-                  c->cyc[vn] && c->cyc[vn + VN_QUICK]->k == c->cyc[vn]->k && c->cyc[vn + VN_QUICK]->fpw == 1)
+                  c->cyc[vn] && !c->cyc[vn]->cta && c->cyc[vn + VN_QUICK]->k == c->cyc[vn]->k && c->cyc[vn + VN_QUICK]->fpw == 1)
                      ? vn + VN_QUICK
                      : vn;
   if (c->cyc[vq]) {
@@ -1022,33 +1025,38 @@ uint64_t ccgpu_sweep_samples(double previous_wer, uint64_t cap) {
 }
 
 // ---- decoding ----------------------------------------------------------------------------------
-int ccgpu_decode_llr(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, const float *y,
-                     uint64_t frames, uint8_t *bits, float *L, uint8_t *iter, uint8_t *failed) {
-  if (!ctx || !code || !y || !bits || !failed) return fail(ctx, CCGPU_ERR_INVALID, "null argument");
-  if (code->ctx != ctx) return fail(ctx, CCGPU_ERR_INVALID, "code was not created on this context");
+// one implementation behind ccgpu_decode_llr (the reference's layout: one byte per decided bit, iter, failed) and
+// ccgpu_decode_llr_packed (compact layout: ceil(n/32) words of decided bits + one status byte per frame)
+static int decode_llr_impl(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, const float *y,
+                           uint64_t frames, uint8_t *bits, float *L, uint8_t *iter, uint8_t *failed, uint32_t *packed,
+                           uint8_t *status) {
   std::lock_guard<std::mutex> g(ctx->mu);
   int rc = check_params(ctx, params);
   if (rc) return rc;
   if (frames == 0) return CCGPU_OK;
   CU(cudaSetDevice(ctx->device));
-  const size_t n = code->spec.n;
+  const size_t n = code->spec.n, npw = (n + 31) / 32;
   MsParams mp{};
   fill_decoder(mp, code, params);
   mp.src = SRC_HBM;
   mp.frames = frames;
   const bool dev = is_device_ptr(y);
   if (dev) {
-    if (!is_device_ptr(bits) || !is_device_ptr(failed) || (L && !is_device_ptr(L)) || (iter && !is_device_ptr(iter)))
+    if ((bits && !is_device_ptr(bits)) || (failed && !is_device_ptr(failed)) || (L && !is_device_ptr(L)) ||
+        (iter && !is_device_ptr(iter)) || (packed && !is_device_ptr(packed)) || (status && !is_device_ptr(status)))
       return fail(ctx, CCGPU_ERR_INVALID, "y is a device pointer: every output must be one too");
     mp.y = y;
     mp.bits = bits;
     mp.L = L;
     mp.iter = iter;
     mp.failed = failed;
+    mp.packed = packed;
+    mp.status = status;
     return launch_ms(ctx, code, params, mp);
   }
-  // host buffers: chunks alternate between two slots so that copies and decoding overlap
-  const size_t per_frame = n * sizeof(float) + n + (L ? n * sizeof(float) : 0) + 2;
+  // host buffers: chunks rotate over the staging slots so that copies and decoding overlap
+  const size_t per_frame = n * sizeof(float) + (L ? n * sizeof(float) : 0) + (packed ? npw * sizeof(uint32_t) : 0) +
+                           (bits ? n : 0) + (iter ? 1 : 0) + (failed ? 1 : 0) + (status ? 1 : 0);
   const uint64_t chunk = std::max<uint64_t>(1024, std::min<uint64_t>((frames + 15) / 16, (size_t(32) << 20) / per_frame));
   rc = ensure_slots(ctx, chunk * per_frame + 256);
   if (rc) return rc;
@@ -1058,28 +1066,54 @@ int ccgpu_decode_llr(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_para
   for (uint64_t f0 = 0; f0 < frames; f0 += chunk, slot = (slot + 1) % kSlots) {
     const uint64_t nf = std::min(chunk, frames - f0);
     cudaStream_t st = ctx->slot_stream[slot];
-    char *base = static_cast<char *>(ctx->slot_buf[slot]);
-    float *d_y = reinterpret_cast<float *>(base);
-    float *d_L = L ? reinterpret_cast<float *>(base + chunk * n * sizeof(float)) : nullptr;
-    uint8_t *d_bits = reinterpret_cast<uint8_t *>(base + chunk * n * sizeof(float) * (L ? 2 : 1));
-    uint8_t *d_iter = d_bits + chunk * n;
-    uint8_t *d_failed = d_iter + chunk;
+    char *at = static_cast<char *>(ctx->slot_buf[slot]);  // 4-byte fields first
+    float *d_y = reinterpret_cast<float *>(at);
+    at += chunk * n * sizeof(float);
+    float *d_L = L ? reinterpret_cast<float *>(at) : nullptr;
+    at += L ? chunk * n * sizeof(float) : 0;
+    uint32_t *d_packed = packed ? reinterpret_cast<uint32_t *>(at) : nullptr;
+    at += packed ? chunk * npw * sizeof(uint32_t) : 0;
+    uint8_t *d_bits = bits ? reinterpret_cast<uint8_t *>(at) : nullptr;
+    at += bits ? chunk * n : 0;
+    uint8_t *d_iter = iter ? reinterpret_cast<uint8_t *>(at) : nullptr;
+    at += iter ? chunk : 0;
+    uint8_t *d_failed = failed ? reinterpret_cast<uint8_t *>(at) : nullptr;
+    at += failed ? chunk : 0;
+    uint8_t *d_status = status ? reinterpret_cast<uint8_t *>(at) : nullptr;
     CU(cudaMemcpyAsync(d_y, y + f0 * n, nf * n * sizeof(float), cudaMemcpyHostToDevice, st));
     mp.y = d_y;
     mp.bits = d_bits;
     mp.L = d_L;
     mp.iter = d_iter;
     mp.failed = d_failed;
+    mp.packed = d_packed;
+    mp.status = d_status;
     mp.frames = nf;
     rc = launch_ms(ctx, code, params, mp, slot);
     if (rc) return rc;
-    CU(cudaMemcpyAsync(bits + f0 * n, d_bits, nf * n, cudaMemcpyDeviceToHost, st));
+    if (bits) CU(cudaMemcpyAsync(bits + f0 * n, d_bits, nf * n, cudaMemcpyDeviceToHost, st));
     if (L) CU(cudaMemcpyAsync(L + f0 * n, d_L, nf * n * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (iter) CU(cudaMemcpyAsync(iter + f0, d_iter, nf, cudaMemcpyDeviceToHost, st));
-    CU(cudaMemcpyAsync(failed + f0, d_failed, nf, cudaMemcpyDeviceToHost, st));
+    if (failed) CU(cudaMemcpyAsync(failed + f0, d_failed, nf, cudaMemcpyDeviceToHost, st));
+    if (packed) CU(cudaMemcpyAsync(packed + f0 * npw, d_packed, nf * npw * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    if (status) CU(cudaMemcpyAsync(status + f0, d_status, nf, cudaMemcpyDeviceToHost, st));
   }
   for (int s = 0; s < kSlots; ++s) CU(cudaStreamSynchronize(ctx->slot_stream[s]));
   return CCGPU_OK;
+}
+
+int ccgpu_decode_llr(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, const float *y,
+                     uint64_t frames, uint8_t *bits, float *L, uint8_t *iter, uint8_t *failed) {
+  if (!ctx || !code || !y || !bits || !failed) return fail(ctx, CCGPU_ERR_INVALID, "null argument");
+  if (code->ctx != ctx) return fail(ctx, CCGPU_ERR_INVALID, "code was not created on this context");
+  return decode_llr_impl(ctx, code, params, y, frames, bits, L, iter, failed, nullptr, nullptr);
+}
+
+int ccgpu_decode_llr_packed(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, const float *y,
+                            uint64_t frames, uint32_t *packed, uint8_t *status) {
+  if (!ctx || !code || !y || !packed || !status) return fail(ctx, CCGPU_ERR_INVALID, "null argument");
+  if (code->ctx != ctx) return fail(ctx, CCGPU_ERR_INVALID, "code was not created on this context");
+  return decode_llr_impl(ctx, code, params, y, frames, nullptr, nullptr, nullptr, nullptr, packed, status);
 }
 
 int ccgpu_awgn_llr(ccgpu_ctx *ctx, uint32_t n, double sigma, uint64_t seed, uint32_t point, uint64_t frame0,

@@ -201,11 +201,20 @@ __global__ void ms_csr_kernel(const __grid_constant__ MsParams p, const CsrView 
     const int nbits = s_flags[1];
     if (p.bits)
       for (int c = tid; c < n; c += nt) p.bits[fr * n + c] = bbuf[c];
+    if (p.packed) {  // compact layout: one thread per 32-bit word of the decided word
+      const int npw = (n + 31) >> 5;
+      for (int w = tid; w < npw; w += nt) {
+        unsigned v = 0u;
+        for (int b = 0; b < 32 && 32 * w + b < n; ++b) v |= (bbuf[32 * w + b] ? 1u : 0u) << b;
+        p.packed[fr * npw + w] = v;
+      }
+    }
     if (p.L)
       for (int c = tid; c < n; c += nt) p.L[fr * n + c] = __fadd_rn(sbuf[c], ybuf[c]);
     if (tid == 0) {
       if (p.iter) p.iter[fr] = static_cast<uint8_t>(failed ? p.max_iter : it);
       if (p.failed) p.failed[fr] = failed ? 1 : 0;
+      if (p.status) p.status[fr] = static_cast<uint8_t>(failed ? 255 : it);
       cnt[C_FRAMES] += 1;
       cnt[C_ITER] += static_cast<unsigned>(failed ? p.max_iter : it + 1);
       cnt[C_FAIL] += failed ? 1 : 0;

@@ -135,6 +135,20 @@ __device__ __forceinline__ unsigned long long binom(unsigned n, unsigned r) {
   return v;
 }
 
+// compact output layout (ccgpu_decode_llr_packed): 32 decided bits of a frame starting at bit `start` of the warp's
+// concatenated decision words bw[0 .. NP) (start = colbase + 32 w for word w of the group's frame), `nbits` of them valid
+template <int NP> __device__ __forceinline__ unsigned extract_word(const unsigned (&bw)[NP], int start, int nbits) {
+  const int idx = start >> 5;
+  unsigned lo = 0u, hi = 0u;
+#pragma unroll
+  for (int ps = 0; ps < NP; ++ps) {
+    lo = (ps == idx) ? bw[ps] : lo;
+    hi = (ps == idx + 1) ? bw[ps] : hi;
+  }
+  const unsigned v = __funnelshift_r(lo, hi, start & 31);
+  return nbits >= 32 ? v : (v & ((1u << nbits) - 1u));
+}
+
 // resident CTAs per SM the register allocation aims at: 8 (64 registers) while the row's messages fit
 template <class S, int VNQ> constexpr int ms_min_blocks() {
   constexpr int VN = VNQ >= VN_QUICK ? VNQ - VN_QUICK : VNQ;
@@ -597,6 +611,12 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VNQ>()) ms_cyclic
         if (is_lead) {
           if (p.iter) p.iter[my_frame] = static_cast<uint8_t>(failed ? p.max_iter : it);
           if (p.failed) p.failed[my_frame] = failed ? 1 : 0;
+          if (p.packed) {
+            constexpr int NPW = (N + 31) >> 5;
+#pragma unroll
+            for (int w = 0; w < NPW; ++w) p.packed[my_frame * NPW + w] = extract_word<NP>(bw, colbase + 32 * w, N - 32 * w);
+          }
+          if (p.status) p.status[my_frame] = static_cast<uint8_t>(failed ? 255 : it);
 #if CCGPU_MS_SMEM_COUNTERS
           cnt_s[0][threadIdx.x] += 1u;
           cnt_s[3][threadIdx.x] += static_cast<unsigned>(it + 1);

@@ -4,9 +4,25 @@
 // Same arithmetic, same order, same outputs as ms_cyclic_kernel (reference codes/soft_decision.h:161-202);
 // the difference is the mapping: one CTA of WPF warps owns ONE frame, thread <-> parity-check row(s)
 // (row = tid + THREADS * i), the W messages of a row stay in registers, y[n] / S[n] / the decided
-// word (as 32-bit masks) live in shared memory, and the steps of the ordered column sum are
-// separated by __syncthreads instead of __syncwarp.  Several CTAs per SM hide the barrier latency.
-// CTAs are persistent and pull frames from the same global queue head.
+// word (as 32-bit masks) live in shared memory.  CTAs are persistent and pull frames from the same
+// global queue head.
+//
+// Ordered column sums (column_sum, soft_decision.h:86-98: a column adds its rows in ascending order, and float
+// addition does not commute with that order), two forms:
+//   * GATHER (ShapeCta::GATHER, one row per thread): every row thread parks its new message of tap j at X[j][row]
+//     in shared memory (one store per edge, immediate offset).  After ONE block barrier the thread that owns
+//     column c adds X[W-1][c - t_{W-1}], ..., X[0][c - t_0] in a register (then X[.][c + N - t_j] for the wrapped
+//     edges of a redundant H): descending taps are ascending rows.  Rows that do not exist are never written and
+//     read +0.0 from the start of the kernel, and S + (+0.0) == S bit for bit because a running sum that started
+//     at +0.0 is never -0.0.  Whether a (column, tap) pair has a row at all is decided PER WARP AT COMPILE TIME
+//     (the column loop is instantiated once per warp index: the 32 columns of a warp and the tap offset are
+//     constants), so only pairs some lane needs are loaded -- 1.2 loads per edge for BCH(255,131) instead of the
+//     2.06 of a dense sweep; the lanes of such a warp that have no row read a zero guard band (32 floats between the
+//     taps' arrays).  All loads are independent; three block barriers per iteration.
+//     With wrap-around, y and S carry a copy of their first TMAX entries behind entry N - 1, so that the row
+//     phase addresses edge (row, tap) at [row + tap] without a wrap test.
+//   * scatter (the shapes whose X does not fit): read-modify-write of S[row + tap_j], the steps separated by
+//     __syncthreads (W per iteration; the kernel is then bound by the barrier latency).
 #pragma once
 #include <cfloat>
 #include <cstdint>
@@ -23,20 +39,79 @@
    measured: 5 (96 registers, 108 bytes spilled) is 7 % slower, an unconstrained allocation (168 registers, 3 CTAs) 12 % slower */
 #endif
 
+#ifndef CCGPU_MS_CTA_SMALL_W
+#define CCGPU_MS_CTA_SMALL_W 32  /* gather shapes with at most this many messages per thread ... */
+#endif
+#ifndef CCGPU_MS_CTA_SMALL_MINBLK
+#define CCGPU_MS_CTA_SMALL_MINBLK 6  /* ... are compiled for this many CTAs per SM */
+#endif
+
 namespace ccgpu {
 
 // the two-rows-per-thread (wrap-around) shapes and the self-correcting flavour need more than 128 registers
-template <class S, int VN> constexpr int ms_cta_min_blocks() { return (S::RPL == 1 && VN != VN_SC) ? CCGPU_MS_CTA_MINBLK : 1; }
+template <class S, int VN> constexpr int ms_cta_min_blocks() {
+  if (S::RPL == 1 && VN != VN_SC && S::GATHER && S::W <= CCGPU_MS_CTA_SMALL_W) return CCGPU_MS_CTA_SMALL_MINBLK;
+  return (S::RPL == 1 && VN != VN_SC) ? CCGPU_MS_CTA_MINBLK : 1;
+}
+
+
+// GATHER column phase of warp WARP (compile time): the warp's columns are c = 32 WARP + THREADS cp + lane.  A
+// (column pass, tap) pair is loaded only if some lane of the warp has a row for it; lanes that have none read the
+// guard band (zero).  Writes S[c] (and its mirror) and the decision masks.
+template <class S, int WARP>
+__device__ __forceinline__ void cta_gather_columns(int tid, int k, const float *xs, const float *ybuf, float *sbuf, unsigned *bword) {
+  constexpr int N = S::N, W = S::W, THREADS = S::THREADS, CPASS = S::CPASS, XS = S::XS;
+  constexpr bool WRAP = S::WRAP;
+  constexpr int KMAX = S::K > 0 ? S::K : (THREADS < N ? THREADS : N);  // rows that can exist
+  using T = typename S::taps;
+  const int lane = tid & 31;
+#pragma unroll
+  for (int cp = 0; cp < CPASS; ++cp) {
+    const int cmin = 32 * WARP + THREADS * cp, cmax = cmin + 31;  // constants after unrolling
+    const int c = cmin + lane;
+    const float *xc = xs + c;
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = W - 1; j >= 0; --j)  // rows c - t_j, ascending as j descends
+      if (cmax - T::get(j) >= 0 && cmin - T::get(j) <= KMAX - 1) acc = __fadd_rn(acc, xc[j * XS - T::get(j)]);
+    if (WRAP) {
+#pragma unroll
+      for (int j = W - 1; j >= 0; --j)  // wrapped edges: rows c + N - t_j
+        if (cmin + N - T::get(j) <= KMAX - 1) acc = __fadd_rn(acc, xc[j * XS + N - T::get(j)]);
+    }
+    bool neg = false;
+    if (c < N) {
+      sbuf[c] = acc;
+      if (WRAP && c < S::TMAX) sbuf[c + N] = acc;
+      neg = __fadd_rn(acc, ybuf[c]) < 0.0f;
+    }
+    const unsigned bal = __ballot_sync(kFull, neg);
+    if (lane == 0) bword[cp * S::WPF + WARP] = bal;
+  }
+  (void)k;
+}
+template <class S, int WARP>
+__device__ __forceinline__ void cta_gather_dispatch(int warp, int tid, int k, const float *xs, const float *ybuf, float *sbuf, unsigned *bword) {
+  if constexpr (WARP < S::WPF) {
+    if (warp == WARP) cta_gather_columns<S, WARP>(tid, k, xs, ybuf, sbuf, bword);
+    else cta_gather_dispatch<S, WARP + 1>(warp, tid, k, xs, ybuf, sbuf, bword);
+  }
+}
 
 template <class S, int VN>
 __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyclic_cta_kernel(const __grid_constant__ MsParams p) {
   constexpr int N = S::N, W = S::W, RPL = S::RPL, NPW = S::NPW, THREADS = S::THREADS, CPASS = S::CPASS;
   constexpr bool WRAP = S::WRAP, SC = VN == VN_SC;
   constexpr int NPAD = NPW * 32;
+  constexpr bool GATHER = S::GATHER;
+  constexpr bool DUP = GATHER && WRAP;     // y / S mirrored behind entry N - 1: no wrap test in the row phase
+  constexpr int XS = S::XS, YW = S::YW;
   using T = typename S::taps;
-  __shared__ float ys[2 * NPAD];  // y[NPAD] then S[NPAD]: edge (row, tap) is yrow[tap] / yrow[NPAD + tap]
+  extern __shared__ float xdyn[];  // GATHER: 32 guard floats, then W arrays of XS floats (rows, then a zero guard band)
+  float *const xs = xdyn + 32;
+  __shared__ float ys[2 * YW];  // y[YW] then S[YW]: edge (row, tap) is yrow[tap] / yrow[YW + tap]
   float *const ybuf = ys;
-  float *const sbuf = ys + NPAD;
+  float *const sbuf = ys + YW;
   __shared__ unsigned bword[CPASS * S::WPF];
   __shared__ long long s_frame;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -50,7 +125,9 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyc
   for (int i = 0; i < RPL; ++i) {
     row[i] = tid + THREADS * i;
     rvalid[i] = row[i] < k;
-    if (!rvalid[i]) row[i] = 0;
+    // threads without a row compute on the addresses of a row that keeps them on their own shared-memory bank
+    // (row 0 would make them collide with the warp's lane 0 on every load) and store nothing
+    if (!rvalid[i]) row[i] = k >= 32 ? lane : 0;
     yrow[i] = ybuf + row[i];
 #pragma unroll
     for (int w = 0; w < NPW; ++w) rmask[i][w] = 0;
@@ -66,6 +143,14 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyc
 
   float r[RPL][W];
   float qold[SC ? RPL : 1][SC ? W : 1];
+  if (GATHER) {
+    for (int x = tid; x < 32 + W * XS; x += THREADS) xdyn[x] = 0.0f;  // what no row writes must read +0.0 for good
+  }
+  float *const xrow = xs + tid;  // GATHER: this thread's slot in every tap's array
+  auto put_y = [&](int c, float v) {
+    ybuf[c] = v;
+    if (DUP && c < S::TMAX) ybuf[c + N] = v;
+  };
   unsigned long long cnt[6] = { 0, 0, 0, 0, 0, 0 };
   long long frame = blockIdx.x;
   constexpr int NBLK = (N + 3) >> 2;
@@ -73,14 +158,14 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyc
   while (frame < static_cast<long long>(p.frames)) {
     // ---------------- frame source
     if (p.src == SRC_HBM) {
-      for (int c = tid; c < N; c += THREADS) ybuf[c] = __ldg(p.y + frame * N + c);
+      for (int c = tid; c < N; c += THREADS) put_y(c, __ldg(p.y + frame * N + c));
     } else if (p.src == SRC_PHILOX) {
       for (int b = tid; b < NBLK; b += THREADS) {
         const float4 v = awgn_block(p.keys, p.point, p.frame0 + static_cast<uint64_t>(frame), b, p.sigma);
         const float vv[4] = { v.x * p.llr_scale, v.y * p.llr_scale, v.z * p.llr_scale, v.w * p.llr_scale };
 #pragma unroll
         for (int e = 0; e < 4; ++e)
-          if (4 * b + e < N) ybuf[4 * b + e] = vv[e];
+          if (4 * b + e < N) put_y(4 * b + e, vv[e]);
       }
     } else if (tid == 0) {
       unsigned long long rank = p.frame0 + static_cast<unsigned long long>(frame);
@@ -93,10 +178,10 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyc
           --ones;
           v = -1.0f;
         }
-        ybuf[c] = v;
+        put_y(c, v);
       }
     }
-    for (int c = tid; c < NPAD; c += THREADS) sbuf[c] = 0.0f;
+    for (int c = tid; c < YW; c += THREADS) sbuf[c] = 0.0f;
 #pragma unroll
     for (int i = 0; i < RPL; ++i)
 #pragma unroll
@@ -127,8 +212,8 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyc
 #pragma unroll
         for (int j = 0; j < W; ++j) {
           int off = T::get(j);
-          if (WRAP && row[i] + off >= N) off -= N;
-          const float s = yrow[i][NPAD + off];
+          if (WRAP && !DUP && row[i] + off >= N) off -= N;
+          const float s = yrow[i][YW + off];
           const float yy = yrow[i][off];
           float e = __fsub_rn(s, r[i][j]);  // scalar adds here: the packed FADD2 form of ms_cyclic.cuh needs aligned
           if (VN == VN_2D) e = __fmul_rn(p.beta_f, e);  // register pairs and spills at this kernel's 128-register budget
@@ -151,7 +236,8 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyc
           par ^= __float_as_uint(q);
         }
         m1v[i] = m1;
-        const float2 g = cn_magnitude_pair(p, m1, m2);
+        float2 g = cn_magnitude_pair(p, m1, m2);
+        if (GATHER && !rvalid[i]) g = make_float2(0.0f, 0.0f);  // no row: its parked messages are +-0.0, which no sum sees
         f1s[i] = xor_sign(g.x, par);
         f2s[i] = xor_sign(g.y, par);
       }
@@ -162,10 +248,14 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyc
           const float q = SC ? qold[i][j] : r[i][j];
           const float f = (fabsf(q) == m1v[i]) ? f2s[i] : f1s[i];
           r[i][j] = xor_sign(f, __float_as_uint(q));
+          if (GATHER) xrow[j * XS] = r[i][j];  // unconditional: a thread without a row parks +-0.0 (see f1s above)
         }
       __syncthreads();
       // ============ column sums, rows ascending
-      for (int c = tid; c < NPAD; c += THREADS) sbuf[c] = 0.0f;
+      if (GATHER) {
+        cta_gather_dispatch<S, 0>(warp, tid, k, xs, ybuf, sbuf, bword);
+      } else {
+      for (int c = tid; c < YW; c += THREADS) sbuf[c] = 0.0f;
       __syncthreads();
 #pragma unroll
       for (int pass = 0; pass < (WRAP ? 2 : 1); ++pass) {
@@ -179,7 +269,7 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyc
               off -= N;
               wrapped = true;
             }
-            if (rvalid[i] && wrapped == (pass == 1)) yrow[i][NPAD + off] = __fadd_rn(yrow[i][NPAD + off], r[i][j]);
+            if (rvalid[i] && wrapped == (pass == 1)) yrow[i][YW + off] = __fadd_rn(yrow[i][YW + off], r[i][j]);
           }
           __syncthreads();
         }
@@ -193,6 +283,7 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyc
         const unsigned bal = __ballot_sync(kFull, neg);
         if (lane == 0) bword[cp * S::WPF + warp] = bal;
       }
+      }  // !GATHER
       __syncthreads();
       bool bad = false;
 #pragma unroll
@@ -219,9 +310,11 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyc
       for (int c = tid; c < N; c += THREADS) p.bits[frame * N + c] = static_cast<uint8_t>((bword[c >> 5] >> (c & 31)) & 1u);
     if (p.L)
       for (int c = tid; c < N; c += THREADS) p.L[frame * N + c] = __fadd_rn(sbuf[c], ybuf[c]);
+    if (p.packed && tid < NPW) p.packed[frame * NPW + tid] = bword[tid];  // columns >= N never vote: the tail bits are 0
     if (tid == 0) {
       if (p.iter) p.iter[frame] = static_cast<uint8_t>(failed ? p.max_iter : it);
       if (p.failed) p.failed[frame] = failed ? 1 : 0;
+      if (p.status) p.status[frame] = static_cast<uint8_t>(failed ? 255 : it);
       cnt[C_FRAMES] += 1;
       cnt[C_ITER] += static_cast<unsigned>(it + 1);
       cnt[C_FAIL] += failed ? 1 : 0;

@@ -15,12 +15,12 @@ template <class S> struct CtaTapTable {
 template <class S> static const CtaTapTable<S> kCtaTapTable{};
 
 template <class S, int VN> MsCyclicEntry make_cta_entry(const char *name) {
-  return MsCyclicEntry{ name, S::N, S::K, S::W, S::RPL, 1, S::NPW, S::WRAP ? 1 : 0, VN, S::THREADS, 1, 1, kCtaTapTable<S>.v,
+  return MsCyclicEntry{ name, S::N, S::K, S::W, S::RPL, 1, S::NPW, S::WRAP ? 1 : 0, VN, S::THREADS, 1, 1, S::DYN_SMEM, kCtaTapTable<S>.v,
                         reinterpret_cast<ms_kernel_fn>(&ms_cyclic_cta_kernel<S, VN>) };
 }
 
 template <class S> MsCyclicEntry make_cta_q_entry(const char *name) {
-  return MsCyclicEntry{ name, S::N, S::K, S::W, S::RPL, 1, S::NPW, S::WRAP ? 1 : 0, VN_FIX, S::THREADS, 1, 2, kCtaTapTable<S>.v,
+  return MsCyclicEntry{ name, S::N, S::K, S::W, S::RPL, 1, S::NPW, S::WRAP ? 1 : 0, VN_FIX, S::THREADS, 1, 2, 0, kCtaTapTable<S>.v,
                         reinterpret_cast<ms_kernel_fn>(&ms_cyclic_cta_q_kernel<S>) };
 }
 

@@ -148,9 +148,11 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_q_min_blocks<S>()) ms_cycli
         if (!__syncthreads_and(allpos)) continue;  // block-uniform
         if (p.bits)
           for (int c = tid; c < N; c += THREADS) p.bits[frame[h] * N + c] = 0;
+        if (p.packed && tid < NPW) p.packed[frame[h] * NPW + tid] = 0u;
         if (tid == 0) {
           if (p.iter) p.iter[frame[h]] = 0;
           if (p.failed) p.failed[frame[h]] = 0;
+          if (p.status) p.status[frame[h]] = 0;
           cnt[C_FRAMES] += 1;
           cnt[C_ITER] += 1;
           s_next[h] = units + static_cast<long long>(atomicAdd(p.work, 1ull));
@@ -281,7 +283,9 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_q_min_blocks<S>()) ms_cycli
           for (int c = tid; c < N; c += THREADS) p.bits[frame[h] * N + c] = static_cast<uint8_t>((bword[h][c >> 5] >> (c & 31)) & 1u);
         if (p.L)
           for (int c = tid; c < N; c += THREADS) p.L[frame[h] * N + c] = __half2float(__ushort_as_half(sbuf16[2 * c + h]));
+        if (p.packed && tid < NPW) p.packed[frame[h] * NPW + tid] = bword[h][tid];
         if (tid == 0) {
+          if (p.status) p.status[frame[h]] = static_cast<uint8_t>(failed ? 255 : it[h]);
           int nbits = 0;
 #pragma unroll
           for (int w = 0; w < NPW; ++w) nbits += __popc(bword[h][w]);

@@ -24,11 +24,11 @@ template <class S> struct TapTable {
 template <class S> static const TapTable<S> kTapTable{};
 
 template <class S, int VN> MsCyclicEntry make_entry(const char *name) {
-  return MsCyclicEntry{ name, S::N, S::K, S::W, S::RPL, S::FPW, S::NP, S::WRAP ? 1 : 0, VN, kMsThreads, 0, 1, kTapTable<S>.v,
+  return MsCyclicEntry{ name, S::N, S::K, S::W, S::RPL, S::FPW, S::NP, S::WRAP ? 1 : 0, VN, kMsThreads, 0, 1, 0, kTapTable<S>.v,
                         reinterpret_cast<ms_kernel_fn>(&ms_cyclic_kernel<S, VN>) };
 }
 template <class S> MsCyclicEntry make_q_entry(const char *name) {
-  return MsCyclicEntry{ name, S::N, S::K, S::W, S::RPL, S::FPW, S::NP, S::WRAP ? 1 : 0, VN_FIX, kMsThreads, 0, 2, kTapTable<S>.v,
+  return MsCyclicEntry{ name, S::N, S::K, S::W, S::RPL, S::FPW, S::NP, S::WRAP ? 1 : 0, VN_FIX, kMsThreads, 0, 2, 0, kTapTable<S>.v,
                         reinterpret_cast<ms_kernel_fn>(&ms_cyclic_q_kernel<S>) };
 }
 

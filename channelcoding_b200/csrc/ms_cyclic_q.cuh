@@ -516,6 +516,13 @@ __global__ void __launch_bounds__(kMsThreads, ms_q_min_blocks<S>()) ms_cyclic_q_
           if (is_lead) {
             if (p.iter) p.iter[my_frame[h]] = static_cast<uint8_t>(failed ? p.max_iter : it[h]);
             if (p.failed) p.failed[my_frame[h]] = failed ? 1 : 0;
+            if (p.packed) {
+              constexpr int NPW = (N + 31) >> 5;
+#pragma unroll
+              for (int w = 0; w < NPW; ++w)
+                p.packed[my_frame[h] * NPW + w] = extract_word<NP>(bw[h], colbase + 32 * w, N - 32 * w);
+            }
+            if (p.status) p.status[my_frame[h]] = static_cast<uint8_t>(failed ? 255 : it[h]);
             cnt_s[0][threadIdx.x] += 1u;
             cnt_s[3][threadIdx.x] += static_cast<unsigned>(it[h] + 1);
             if (failed || nbits != 0) {

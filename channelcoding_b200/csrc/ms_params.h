@@ -52,6 +52,8 @@ struct MsParams {
   float *L;            // frames x n
   uint8_t *iter;       // frames
   uint8_t *failed;     // frames
+  uint32_t *packed;    // compact layout: frames x ceil(n/32) words, bit (c & 31) of word (c >> 5) = decision of column c
+  uint8_t *status;     // compact layout: frames, iteration index at which the stop test passed, 255 = failure
   unsigned long long *counters;  // kCounterSlots, accumulated with atomics
   unsigned long long *work;      // dynamic frame queue head, zeroed by the host before the launch
   unsigned work_batch;            // most frame indices a warp takes from the queue per atomic (>= 1)
@@ -82,6 +84,7 @@ struct MsCyclicEntry {
   int threads;  // CTA size
   int cta;      // 0: ms_cyclic_kernel (warp owns frames), 1: ms_cyclic_cta_kernel (CTA owns one frame)
   int slots;    // frames a lane / thread works on at once (2 for the fixed-point kernels, else 1)
+  int dyn_smem; // cta == 1: bytes of dynamic shared memory the kernel needs (gather buffer of the float CTA kernel)
   const int *taps;
   ms_kernel_fn fn;
 };

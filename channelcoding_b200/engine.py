@@ -245,6 +245,27 @@ class Code:
                                                     _ptr(L), _ptr(it), _ptr(failed)))
         return bits, L, it, failed
 
+    def decode_packed(self, y, variant="MS", alpha=1.0, beta=0.0, max_iter=50, stop_rule=STOP_REF_ZERO_OVERLAP, out=None,
+                      quant=None):
+        """ccgpu_decode_llr_packed: compact outputs -> packed (frames, ceil(n/32)) uint32, status (frames,) uint8
+        [iteration index, 255 = failure]; numpy or torch like decode()"""
+        p = ms_params(variant, alpha, beta, max_iter, stop_rule, quant)
+        npw = (self.n + 31) // 32
+        if _is_torch(y):
+            import torch
+            y = y.contiguous().view(-1, self.n)
+            frames = y.shape[0]
+            packed, status = out if out is not None else (torch.empty((frames, npw), dtype=torch.int32, device=y.device),
+                                                          torch.empty(frames, dtype=torch.uint8, device=y.device))
+        else:
+            y = np.ascontiguousarray(y, np.float32).reshape(-1, self.n)
+            frames = y.shape[0]
+            packed, status = out if out is not None else (np.empty((frames, npw), np.uint32), np.empty(frames, np.uint8))
+        self.ctx._follow_torch(y, packed)
+        self.ctx._check(_lib.lib().ccgpu_decode_llr_packed(self.ctx._h, self._h, C.byref(p), _ptr(y), frames, _ptr(packed),
+                                                           _ptr(status)))
+        return packed, status
+
     def awgn_point(self, ebno_db, frames, variant="MS", alpha=1.0, beta=0.0, max_iter=50,
                    stop_rule=STOP_REF_ZERO_OVERLAP, seed=0, point=0, frame0=0, out=None, quant=None):
         """one Eb/N0 point of awgn_simulation (simulation.c++:112-149), fused on the GPU -> counters.

@@ -193,6 +193,15 @@ int ccgpu_encode(const ccgpu_code *code, const uint8_t *msgs, uint64_t count, ui
 int ccgpu_decode_llr(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, const float *y,
                      uint64_t frames, uint8_t *bits, float *L, uint8_t *iter, uint8_t *failed);
 
+/* the same decode with a COMPACT output layout (opt-in; the byte-per-bit layout above is what correct() returns,
+ * simulation/simulation.h:62-65, this one is what a batch consumer needs): the algorithmic output of SURVEY.md 8(d),
+ * 4 * ceil(n/32) bytes of decided bits + one status byte per frame instead of n + 2 bytes.
+ *   packed  frames x ceil(n/32) uint32   bit (c & 31) of word (c >> 5) is the decision of column c; unused bits 0
+ *   status  frames                       0-based iteration index at which the stop test passed, 255 = decoding_failure
+ * (max_iter <= 255, so a passing index is at most 254).  Host or device pointers like ccgpu_decode_llr. */
+int ccgpu_decode_llr_packed(ccgpu_ctx *ctx, const ccgpu_code *code, const ccgpu_ms_params *params, const float *y,
+                            uint64_t frames, uint32_t *packed, uint8_t *status);
+
 /* sigma of simulation.c++:83-85: 1 / sqrt(2 * rate * 10^(ebno_db/10)) */
 double ccgpu_sigma(double rate, double ebno_db);
 /* Shannon limit Eb/N0 [dB] of the binary-input AWGN channel at `rate` exactly as the reference looks it up: ebno(rate)

@@ -810,3 +810,44 @@ def test_every_compiled_shape_keeps_the_reference_order(ctx, catalogue):
                         "%s %s" % (name, variant))
         seen += 1
     assert seen >= 16
+
+
+@pytest.mark.parametrize("name", ["bch_15_7", "bch_31_16", "bch_63_36", "bch_127_64", "bch_255_131", "bch_63_57"])
+def test_packed_output_layout(ctx, name, catalogue):
+    """ccgpu_decode_llr_packed (compact layout: ceil(n/32) words of decided bits + one status byte per frame, the
+    algorithmic output of SURVEY 8d) carries exactly the information of ccgpu_decode_llr on every kernel: several
+    frames per warp, several rows per lane, CTA per frame, the general (CSR) kernel, float and fixed-point flavours,
+    host and device buffers"""
+    import torch
+    e = catalogue[name]
+    code = make_code(ctx, e)
+    n = e["n"]
+    npw = (n + 31) // 32
+    rng = np.random.default_rng(zlib.crc32(("packed" + name).encode()))
+    frames = 3001 if n <= 63 else (301 if n <= 127 else 61)
+    y = (1 + oracle.sigma(e["rate"], 4.0) * rng.standard_normal((frames, n))).astype(np.float32)
+    y[0] = -1.0   # all-one word
+    y[1, ::2] = -1.0
+    codes = [code]
+    if n == 63 and name == "bch_63_36":
+        codes.append(ctx.from_dense(code.H()[rng.permutation(code.h_rows)], e["rate"]))  # CSR kernel
+    quant = (8.0, 31, 29 if n == 255 else 31)
+    for c in codes:
+        for variant, alpha, mi, stop in (("NMS", 0.8, 50, 0), ("MS", 1.0, 7, 1), ("SCMS2", 1.0, 20, 2), ("NMS_Q", 0.8, 50, 0),
+                                         ("MS_Q", 1.0, 6, 1)):
+            if variant.endswith("_Q") and c.kernel != 1:
+                continue
+            q = quant if variant.endswith("_Q") else None
+            bits, _, it, failed = c.decode(y, variant, alpha, 0.0, mi, stop, want_L=False, quant=q)
+            packed, status = c.decode_packed(y, variant, alpha, 0.0, mi, stop, quant=q)
+            assert packed.shape == (frames, npw) and packed.dtype == np.uint32
+            unpacked = ((packed[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(frames, npw * 32).astype(np.uint8)
+            what = "%s %s kernel %d" % (name, variant, c.kernel)
+            assert np.array_equal(unpacked[:, :n], bits), what
+            assert not unpacked[:, n:].any(), what + ": unused bits must be zero"
+            assert np.array_equal(status, np.where(failed == 1, 255, it).astype(np.uint8)), what
+            if c is code and variant in ("NMS", "NMS_Q"):
+                yt = torch.from_numpy(y).cuda()
+                pk, st = c.decode_packed(yt, variant, alpha, 0.0, mi, stop, quant=q)
+                ctx.sync()
+                assert np.array_equal(pk.cpu().numpy().view(np.uint32), packed) and np.array_equal(st.cpu().numpy(), status), what

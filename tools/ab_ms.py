@@ -17,6 +17,8 @@ def main():
     ap.add_argument("--variant", default="NMS")
     ap.add_argument("--alpha", type=float, default=0.8)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--rows", type=int, default=0, help="redundant H: this many cyclic shifts (ccgpu_code_set_rows)")
+    ap.add_argument("--stop", type=int, default=0)
     a = ap.parse_args()
     import numpy as np
     import torch
@@ -24,6 +26,8 @@ def main():
     ctx = cc.Context(0)
     ctx.use_torch_stream()
     code = ctx.bch(a.q, errors=a.t)
+    if a.rows:
+        code.set_rows(a.rows)
     y = torch.empty((a.frames, code.n), dtype=torch.float32, device="cuda")
     ctx.awgn_llr(code.n, np.float32(cc.sigma(code.rate, a.ebno)), 0, 1, 0, a.frames, out=y)
     out = (torch.empty((a.frames, code.n), dtype=torch.uint8, device="cuda"), None,
@@ -32,7 +36,7 @@ def main():
     for _ in range(a.reps + 2):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        code.decode(y, a.variant, a.alpha, 0.0, 50, out=out, want_L=False)
+        code.decode(y, a.variant, a.alpha, 0.0, 50, a.stop, out=out, want_L=False)
         e1.record()
         torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
@@ -41,12 +45,14 @@ def main():
     for _ in range(a.reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        code.awgn_point(a.ebno, a.frames, a.variant, a.alpha, 0.0, 50, out=cnt)
+        code.awgn_point(a.ebno, a.frames, a.variant, a.alpha, 0.0, 50, a.stop, out=cnt)
         e1.record()
         torch.cuda.synchronize()
         bestf = min(bestf, e0.elapsed_time(e1))
-    print("%s n=%d %s %.1f dB: resident %.4e frames/s (%.3f ms)   fused %.4e frames/s   checksum %d" % (
-        os.environ.get("CCGPU_LIB", "libccgpu.so").split("/")[-1], code.n, a.variant, a.ebno, a.frames / best * 1e3, best,
+    it = torch.where(out[3] == 1, torch.full_like(out[2], 50).int(), out[2].int() + 1).double().mean().item()
+    print("%s n=%d rows=%d %s %.1f dB: %.2f it, %.3e edge-it/s resident | resident %.4e frames/s (%.3f ms)   fused %.4e frames/s   checksum %d" % (
+        os.environ.get("CCGPU_LIB", "libccgpu.so").split("/")[-1], code.n, code.h_rows, a.variant, a.ebno, it,
+        a.frames / best * 1e3 * it * code.edges, a.frames / best * 1e3, best,
         a.frames / bestf * 1e3, int(out[2].sum().item()) + int(out[3].sum().item())))
 
 
