@@ -173,6 +173,153 @@ def cpu_reference_rs(q, errors, words):
     return len(words) / (time.perf_counter() - t0)
 
 
+def other_configs(ctx, torch, dist, np, world, rank, dev, timed, args):
+    """the other BASELINE.json configurations (bench.py's headline is configs[1]), one short measurement each in the same
+    run so that the driver's BENCH / SCALE records carry them: every rank works on its own frames (weak scaling, no
+    data-path collective), CUDA events on the launching stream, max over ranks.  Rank 0 adds the reference's CPU decoder
+    of the same code on the host cores (a few seconds each) and the roofline figures -> list of records"""
+    hbm_peak, sm_max, which = measured_peaks()
+    alu_peak = 148 * 128 * sm_max * 1e6
+    out = []
+    cnt = torch.zeros(8, dtype=torch.int64, device=dev)
+
+    def point(config, kernel, code, ebno, frames, variant, alpha=0.8, stop=0, quant=None, steps=3, cpu=None, note=None):
+        state = {"s": 0}
+        pt = int(round(ebno * 2)) + 64
+
+        def step():
+            f0 = (state["s"] * world + rank) * frames
+            code.awgn_point(ebno, frames, variant, alpha, 0.0, MAX_ITER, stop, seed=3, point=pt, frame0=f0, out=cnt, quant=quant)
+            state["s"] += 1
+        cnt.zero_()
+        ms = timed(step, steps, 1)
+        c = cnt.clone()
+        if world > 1:
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        c = c.cpu().numpy()
+        done = int(c[0])
+        value = world * frames * steps / (ms * 1e-3)
+        iters = float(c[3]) / max(1, done)
+        rec = {"config": config, "path": "ccgpu_awgn_point (Philox channel + decode + counters fused)", "kernel": kernel,
+               "ebno_db": ebno, "variant": variant, "value": value, "unit": "frames/s", "info_bits_per_s": value * code.l,
+               "ms_per_step": ms / steps, "frames_per_step_per_gpu": frames, "n_gpus": world,
+               "wer": float(c[1]) / max(1, done), "ber": float(c[2]) / max(1, done) / code.n, "avg_iterations": iters,
+               "edge_iterations_per_s": value * iters * code.edges,
+               # SURVEY 8(d): the decoders are on-chip bound; HBM fraction as the contract asks, lane-op model beside it
+               "roofline": {"bound": "hbm", "achieved": value / world * (4 * code.n + 4 * ((code.n + 31) // 32) + 4) / 1e9,
+                            "peak": hbm_peak, "unit": "GB/s",
+                            "frac": value / world * (4 * code.n + 4 * ((code.n + 31) // 32) + 4) / 1e9 / hbm_peak,
+                            "traffic": 0, "note": "fused point: no LLR ever reaches HBM; bytes are what the streaming "
+                                                  "form of the same decode would move"},
+               "alu": {"model": "avg_iters*(11E+2n) lane-ops/frame (SURVEY 8d)",
+                       "frac": value / world * iters * (11 * code.edges + 2 * code.n) / alu_peak}}
+        if note:
+            rec["note"] = note
+        if rank == 0 and cpu is not None and not args.no_cpu:
+            r = cpu_reference_point(*cpu, ebno, 3.0)
+            if r is not None:
+                f, w, el = r
+                rec["cpu_baseline"] = {"value": f / el, "unit": "frames/s", "cores": os.cpu_count(), "kind": "reference",
+                                       "sample": "3 s wall = %d frames, WER %.4f" % (f, w / max(1, f))}
+        out.append(rec)
+
+    # ---- configs[0]: BCH(15,7) sum-product, Eb/N0 1..6 dB
+    c15 = ctx.bch(4, errors=2)
+    for eb in (1.0, 3.0, 6.0):
+        point("configs[0] BCH(15,7) t=2 sum-product BP", "ms_cyclic_kernel<bch_15_7, VN_SPA>", c15, eb, 1 << 24, "SPA", 1.0, stop=1,
+              cpu=(4, 2, 0) if eb == 3.0 else None,
+              note="the reference has no sum-product decoder: cpu_baseline is its min-sum decoder of the same code")
+    # ---- configs[2]: BCH(127,64), H(), redundant H (127 cyclic shifts), multiple bases
+    c127 = ctx.bch(7, errors=10)
+    point("configs[2] BCH(127,64) t=10 NMS on H() (63 rows)", "ms_cyclic_kernel<bch_127_64, VN_PLAIN>", c127, 5.0, 1 << 20, "NMS",
+          cpu=(7, 10, 1))
+    point("configs[2] BCH(127,64) t=10 NMS_Q on H() (63 rows)", "ms_cyclic_q_kernel<bch_127_64>", c127, 5.0, 1 << 20, "NMS_Q",
+          quant=(8.0, 31, 31))
+    c127.set_rows(127)
+    point("configs[2] BCH(127,64) t=10 NMS on the redundant H (127 cyclic-shift rows)",
+          "ms_cyclic_cta_kernel<bch_127_64_red_cta, VN_PLAIN>", c127, 5.0, 1 << 19, "NMS", stop=1)
+    point("configs[2] BCH(127,64) t=10 NMS_Q on the redundant H (127 cyclic-shift rows)",
+          "ms_cyclic_cta_q_kernel<bch_127_64_red_cta>", c127, 5.0, 1 << 19, "NMS_Q", stop=1, quant=(8.0, 31, 31))
+    c127.set_rows(63)
+    nb, fr = 8, 1 << 18
+    shifts = [(127 * i) // nb for i in range(nb)]
+    state = {"s": 0, "c": None}
+
+    def step_mbbp():
+        state["c"] = c127.awgn_point_mbbp(5.0, fr, shifts, "NMS", 0.8, stop_rule=1, seed=3, point=99,
+                                          frame0=(state["s"] * world + rank) * fr)
+        state["s"] += 1
+    ms = timed(step_mbbp, 3, 1)
+    c = state["c"]
+    out.append({"config": "configs[2] BCH(127,64) t=10 NMS, 8 bases (rotations of H), best converged candidate kept",
+                "path": "ccgpu_awgn_point_mbbp (channel kernel -> rotate -> decode -> select -> count)",
+                "kernel": "ms_cyclic_kernel<bch_127_64, VN_PLAIN> on 8 x frames candidates", "ebno_db": 5.0, "variant": "NMS",
+                "value": world * fr * 3 / (ms * 1e-3), "unit": "frames/s", "candidate_decodes_per_s": nb * world * fr * 3 / (ms * 1e-3),
+                "ms_per_step": ms / 3, "frames_per_step_per_gpu": fr, "n_gpus": world,
+                "wer": c["frame_errors"] / max(1, c["frames"]), "wer_note": "last step of rank 0"})
+    # ---- configs[4]: BCH(255,131) NMS
+    c255 = ctx.bch(8, errors=18)
+    point("configs[4] BCH(255,131) t=18 NMS", "ms_cyclic_cta_kernel<bch_255_131_cta, VN_PLAIN>", c255, 6.0, 1 << 18, "NMS",
+          cpu=(8, 18, 1))
+    point("configs[4] BCH(255,131) t=18 NMS", "ms_cyclic_cta_kernel<bch_255_131_cta, VN_PLAIN>", c255, 8.0, 1 << 20, "NMS")
+    point("configs[4] BCH(255,131) t=18 NMS_Q", "ms_cyclic_cta_q_kernel<bch_255_131_cta>", c255, 6.0, 1 << 18, "NMS_Q",
+          quant=(8.0, 31, 29))
+    # ---- configs[3]: RS(255,223), 1e7 codewords over the job (at least 2.5e6 per GPU), 0..17 symbol errors
+    rs = ctx.rs(8, 16)
+    count = max(10_000_000 // world, 2_500_000)
+    rng = np.random.default_rng(5)
+    base = 4096
+    words = rs.encode(rng.integers(0, 256, size=(base, rs.l)).astype(np.uint8))
+    bad = words.copy()
+    ne = rng.integers(0, 18, size=base)
+    for i in range(base):
+        pos = rng.choice(255, ne[i], replace=False)
+        bad[i, pos] ^= rng.integers(1, 256, size=ne[i]).astype(np.uint8)
+    d_words = torch.from_numpy(bad).to(dev).repeat((count + base - 1) // base, 1)[:count].contiguous()
+    o = (torch.empty_like(d_words), torch.empty(count, dtype=torch.uint8, device=dev), torch.empty(count, dtype=torch.uint8, device=dev))
+    ms = timed(lambda: rs.gf_decode(d_words, out=o), 3, 1)
+    ok = o[2][:base].cpu().numpy() == 0
+    assert np.array_equal(o[0][:base].cpu().numpy()[ok], words[ok]) and ok[ne <= 16].all() and not ok[ne > 16].any()
+    value = world * count * 3 / (ms * 1e-3)
+    ncu_rec, current = ncu_capture("K4 gf_decode RS(255,223) 0..17 errors")
+    wf = ncu_rec.get("smem_wavefronts_per_unit") if (ncu_rec and current) else None
+    rec = {"config": "configs[3] RS(255,223) over GF(2^8) batched hard decode, 1e7 codewords, 0..17 symbol errors (t = 16)",
+           "path": "ccgpu_gf_decode, words resident in HBM", "kernel": "gf_decode_kernel", "value": value, "unit": "codewords/s",
+           "ms_per_step": ms / 3, "codewords_per_step_per_gpu": count, "n_gpus": world,
+           "roofline": {"bound": "hbm", "achieved": value / world * 511 / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": value / world * 511 / 1e9 / hbm_peak, "bytes_per_codeword": 511,
+                        "traffic": (ncu_rec.get("dram_bytes_per_unit") * count) if (ncu_rec and current and ncu_rec.get("dram_bytes_per_unit")) else None},
+           # the pipe that binds: table lookups in shared memory, one wavefront per SM per cycle
+           "smem": {"wavefronts_per_codeword": wf, "frac": (value / world * wf / (148 * sm_max * 1e6)) if wf else None,
+                    "capture": "profiles/r2_kernels.json" if (ncu_rec and current) else "no ncu capture of the current sources"}}
+    del d_words, o
+    # end to end: host buffers through the C ABI (chunked H2D / decode / D2H pipeline)
+    nh = count // 4
+    h_words = torch.from_numpy(bad).repeat((nh + base - 1) // base, 1)[:nh].contiguous().pin_memory()
+    h_out = (torch.empty((nh, 255), dtype=torch.uint8).pin_memory().numpy(), torch.empty(nh, dtype=torch.uint8).pin_memory().numpy(),
+             torch.empty(nh, dtype=torch.uint8).pin_memory().numpy())
+    hw = h_words.numpy()
+    rs.gf_decode(hw, out=h_out)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        rs.gf_decode(hw, out=h_out)
+    el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    rec["e2e"] = {"value": world * nh * 3 / float(el.item()), "unit": "codewords/s", "h2d_bytes_per_step": nh * 255,
+                  "d2h_bytes_per_step": nh * 257, "path": "ccgpu_gf_decode with pinned host buffers"}
+    if rank == 0 and not args.no_cpu:
+        r = cpu_reference_rs(8, 16, bad[:2048])
+        if r is not None:
+            rec["cpu_baseline"] = {"value": r, "unit": "codewords/s", "cores": 1, "kind": "reference",
+                                   "sample": "2048 of the same words, euklid_tag, one thread (x %d cores = %.3g if every core ran one)"
+                                             % (os.cpu_count(), r * os.cpu_count())}
+    out.append(rec)
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -215,6 +362,7 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=1 << 22, help="frames per step per GPU for the host-buffer path")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the table of the other BASELINE.json configurations")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -363,6 +511,8 @@ def main():
     cnt = counters.cpu().numpy()
     fused_value = world * B * args.steps / (ms_fused * 1e-3)
 
+    table = None if args.no_configs else other_configs(ctx, torch, dist, np, world, rank, dev, timed, args)
+
     if rank == 0:
         hbm_peak, sm_max, which = measured_peaks()
         kernel_ms = ms_res / args.steps
@@ -420,6 +570,8 @@ def main():
             "fixed_point": fixed,
             "clocks": clocks,
         }
+        if table is not None:
+            line["baseline_configs"] = table
         if not args.no_cpu:
             rate, cores, kind, werr, frames = cpu_reference(args.ebno, args.cpu_seconds)
             line["cpu_baseline"] = {"value": rate, "unit": "frames/s", "cores": cores, "kind": kind,

@@ -51,5 +51,15 @@ def test_gpu_arm_contract():
         assert 0 < d["smem"]["frac"] < 1 and 0 < d["issue"]["frac"] < 1 and d["roofline"]["traffic"] > 0
     else:
         assert d["smem"]["frac"] is None and d["issue"]["frac"] is None and d["roofline"]["traffic"] is None
+    # the other BASELINE.json configurations ride in the same line (driver-visible): sum-product BCH(15,7), BCH(127,64) on
+    # H / redundant H / multiple bases, RS(255,223) with its roofline, BCH(255,131)
+    table = d["baseline_configs"]
+    names = " | ".join(t["config"] for t in table)
+    for key in ("configs[0] BCH(15,7)", "configs[2] BCH(127,64)", "redundant H", "8 bases", "configs[3] RS(255,223)", "configs[4] BCH(255,131)"):
+        assert key in names, key
+    assert all(t["value"] > 0 and t["n_gpus"] == 1 for t in table)
+    rs = [t for t in table if "RS(255,223)" in t["config"]][0]
+    assert rs["roofline"]["bytes_per_codeword"] == 511 and 0 < rs["roofline"]["frac"] < 1 and rs["e2e"]["value"] > 0
+    assert rs["cpu_baseline"]["value"] > 0 and any("cpu_baseline" in t for t in table if "BCH(255,131)" in t["config"])
     ref = run(["--impl", "reference", "--steps", "1", "--warmup", "0"])
     assert ref["config"]["workload"] == d["config"]["workload"] and ref["metric"] == d["metric"] and ref["unit"] == d["unit"]
