@@ -444,7 +444,8 @@ void select_cyclic(ccgpu_code *c) {
   for (int vn = 0; vn < VN_COUNT; ++vn) {
     if (!c->cyc[vn]) continue;
     c->smem[vn] = c->cyc[vn]->cta ? size_t(c->cyc[vn]->dyn_smem) : size_t(kMsThreads / 32) * 2 * 32 * c->cyc[vn]->np * sizeof(float);
-    if (c->smem[vn] > 48 * 1024)
+    // opt in whenever static + dynamic shared memory may pass 48 KB (the CTA kernels keep y / S / staging rows static)
+    if (c->smem[vn] > 32 * 1024)
       cudaFuncSetAttribute(reinterpret_cast<const void *>(c->cyc[vn]->fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                            static_cast<int>(c->smem[vn]));
     int occ = 0;
@@ -568,6 +569,9 @@ int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsP
   // the fixed-point kernels test for all-positive frames at run time when the hint is set; with several frames per
   // warp all of them must be all-positive at once, which is rare: measured slower there (profiles/r2_notes.md)
   if (vn == VN_FIX && c->cyc[VN_FIX] && !c->cyc[VN_FIX]->cta && c->cyc[VN_FIX]->fpw != 1) mp.quick_hint = 0;
+  // the float CTA kernel screens groups of frames at any Eb/N0 (ms_cyclic_cta.cuh, grouped mode): no cost where no frame
+  // is all-positive, measured in profiles/r2_notes.md
+  if (c->cyc[vn] && c->cyc[vn]->cta && mp.src == SRC_PHILOX) mp.quick_hint = 1;
   if (ctx->opt_quick >= 0) mp.quick_hint = ctx->opt_quick;
   const int vq = (mp.quick_hint && vn != VN_SPA && vn != VN_FIX && mp.L == nullptr && p->stop_rule != CCGPU_STOP_NONE && c->cyc[vn + VN_QUICK] &&
                   c->cyc[vn] && !c->cyc[vn]->cta && c->cyc[vn + VN_QUICK]->k == c->cyc[vn]->k && c->cyc[vn + VN_QUICK]->fpw == 1)

@@ -162,6 +162,7 @@ template <class S, int VNQ> constexpr int ms_min_blocks() {
 template <class S, int VNQ>
 __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VNQ>()) ms_cyclic_kernel(const __grid_constant__ MsParams p) {
   constexpr bool QUICK = VNQ >= VN_QUICK;                   // see quick_ok below
+  constexpr int NBLK = (S::N + 3) >> 2;                     // Philox blocks (four channel values each) per frame
   constexpr int VN = QUICK ? VNQ - VN_QUICK : VNQ;
   constexpr int N = S::N, W = S::W, RPL = S::RPL, NP = S::NP, FPW = S::FPW;
   constexpr bool WRAP = S::WRAP, SC = VN == VN_SC, SPA = VN == VN_SPA;
@@ -269,7 +270,6 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VNQ>()) ms_cyclic
 #else
   unsigned cnt_frames = 0, cnt_ferr = 0, cnt_berr = 0, cnt_iter = 0, cnt_fail = 0, cnt_und = 0;
 #endif
-  constexpr int NBLK = (N + 3) >> 2;
   static_assert(FPW <= 8, "grant slots");
   __shared__ long long pool_next_s[kMsThreads / 32];  // frame indices already taken from the queue: next one ..
   __shared__ int pool_left_s[kMsThreads / 32];        // .. and how many are left
@@ -332,6 +332,20 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VNQ>()) ms_cyclic
   // because the extra branch costs the plain kernel 3 % at 4 dB (register allocation at the 64-register cap); the
   // host picks it when enough such frames are expected (api.cu launch_ms).
   const bool quick_ok = QUICK && p.L == nullptr && p.stop_rule != STOP_NONE && p.max_iter >= 1;
+  // SCREENING (QUICK flavour, one frame per warp, Monte-Carlo points that want counters only): the warp draws frames in
+  // passes of FP = 32 / NBLK -- every lane generates ONE Philox block, so all lanes work (16 of 32 did for n = 63) --
+  // parks the values in a staging row and looks at the signs.  All-positive frames are counted and forgotten: no y / S
+  // initialisation, no message reset, no trip through the iteration loop, no queue bookkeeping (about 230 warp
+  // instructions per such frame before, about 60 now).  The frames that need the decoder are then taken from the staging
+  // row one after the other.  Same counters as any other schedule: the noise is keyed by the frame index.
+  constexpr bool SCREEN = QUICK && FPW == 1 && NBLK <= 32;
+  constexpr int FP = SCREEN ? 32 / NBLK : 1;  // frames per screening pass
+  const bool screen_on = SCREEN && quick_ok && p.src == SRC_PHILOX && p.counters != nullptr && p.bits == nullptr && p.iter == nullptr &&
+                         p.failed == nullptr && p.packed == nullptr && p.status == nullptr;
+  __shared__ __align__(16) float stage_s[SCREEN ? kMsThreads / 32 : 1][SCREEN ? 128 : 4];  // FP frames of 4 * NBLK values
+  __shared__ long long stage_idx_s[SCREEN ? kMsThreads / 32 : 1][FP];
+  unsigned hardmask = 0;   // staged frames that still need the decoder
+  bool first_pass = true;  // the first staged frame of a warp is its statically assigned one
 
   while (true) {
     if (__ballot_sync(kFull, active) == 0u) break;
@@ -339,7 +353,103 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VNQ>()) ms_cyclic
 
     // ============ (re)fill frame groups that finished
     const unsigned initm = __ballot_sync(kFull, active && need_init);
-    if (initm) {
+    if (SCREEN && screen_on) {
+      if (active && need_init) {  // warp-uniform: one frame per warp
+        __syncwarp();
+        for (;;) {
+          if (hardmask == 0u) {  // ---- a new screening pass
+            if (lane == 0) {
+              int left = pool_left_s[warp_in_cta];
+              long long nx = pool_next_s[warp_in_cta];
+#pragma unroll
+              for (int f = 0; f < FP; ++f) {
+                if (first_pass && f == 0) {
+                  stage_idx_s[warp_in_cta][0] = my_frame;
+                  continue;
+                }
+                if (left == 0) {
+                  left = static_cast<int>(guided_batch(p, nx, pool_batch_s[warp_in_cta]));
+                  pool_batch_s[warp_in_cta] = static_cast<unsigned>(left);
+                  nx = units + static_cast<long long>(atomicAdd(p.work, static_cast<unsigned long long>(left)));
+                }
+                stage_idx_s[warp_in_cta][f] = nx++;
+                --left;
+              }
+              pool_next_s[warp_in_cta] = nx;
+              pool_left_s[warp_in_cta] = left;
+            }
+            first_pass = false;
+            __syncwarp();
+            const int f = lane / NBLK, blk = lane - f * NBLK;
+            const long long fr = f < FP ? stage_idx_s[warp_in_cta][f] : static_cast<long long>(p.frames);
+            bool nonpos = false;
+            if (fr < static_cast<long long>(p.frames)) {
+              const float4 v = awgn_block(p.keys, p.point, p.frame0 + static_cast<uint64_t>(fr), blk, p.sigma);
+              const float4 sv = make_float4(v.x * p.llr_scale, v.y * p.llr_scale, v.z * p.llr_scale, v.w * p.llr_scale);
+              nonpos = !(sv.x > 0.0f) || (4 * blk + 1 < N && !(sv.y > 0.0f)) || (4 * blk + 2 < N && !(sv.z > 0.0f)) ||
+                       (4 * blk + 3 < N && !(sv.w > 0.0f));
+              *reinterpret_cast<float4 *>(&stage_s[warp_in_cta][4 * lane]) = sv;
+            }
+            const unsigned npm = __ballot_sync(kFull, nonpos);
+            unsigned nquick = 0, nvalid = 0;
+#pragma unroll
+            for (int g = 0; g < FP; ++g) {
+              if (stage_idx_s[warp_in_cta][g] < static_cast<long long>(p.frames)) {
+                ++nvalid;
+                constexpr unsigned gm = NBLK >= 32 ? kFull : ((1u << NBLK) - 1u);
+                if (npm & (gm << (g * NBLK))) hardmask |= 1u << g;
+                else ++nquick;
+              }
+            }
+            if (lane == 0 && nquick) {  // iteration 0 decides them: one iteration each, no errors
+#if CCGPU_MS_SMEM_COUNTERS
+              cnt_s[0][threadIdx.x] += nquick;
+              cnt_s[3][threadIdx.x] += nquick;
+#else
+              cnt_frames += nquick;
+              cnt_iter += nquick;
+#endif
+            }
+            if (nvalid == 0u) {  // the queue is exhausted
+              active = false;
+              break;
+            }
+            __syncwarp();
+            if (hardmask == 0u) continue;
+          }
+          // ---- the next staged frame that needs the decoder
+          const int f = __ffs(hardmask) - 1;
+          hardmask &= hardmask - 1u;
+          my_frame = stage_idx_s[warp_in_cta][f];
+#pragma unroll
+          for (int ps = 0; ps < NP; ++ps) {
+            const int c = lane + 32 * ps;
+            if (c < N) {
+              ybuf[c] = stage_s[warp_in_cta][f * 4 * NBLK + c];
+              sbuf[c] = 0.0f;
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < RPL; ++i)
+#pragma unroll
+            for (int j = 0; j < W; ++j) {
+              r[i][j] = 0.0f;
+              if (SC || SPA) qold[i][j] = 0.0f;
+            }
+          it = 0;
+          need_init = false;
+          break;
+        }
+        __syncwarp();
+        if (YREG && active) {
+#pragma unroll
+          for (int i = 0; i < RPL; ++i)
+#pragma unroll
+            for (int j = 0; j < YN; ++j) yreg[i][j] = yrow[i][T::get(j)];
+        }
+      }
+      if (!active) continue;  // exhausted: the loop head ends the warp
+    } else if (initm) {
       __syncwarp();  // the finished frame's y / S were read by other lanes (outputs): order those reads first
       if (p.src == SRC_HBM) {
 #pragma unroll
@@ -636,11 +746,15 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VNQ>()) ms_cyclic
 #endif
         }
       }
-      next = take_frames(fin);
-      if (fin) {
-        my_frame = next;
-        active = my_frame < static_cast<long long>(p.frames);
-        need_init = true;
+      if (SCREEN && screen_on) {
+        if (fin) need_init = true;  // the refill above finds the warp's next frame
+      } else {
+        next = take_frames(fin);
+        if (fin) {
+          my_frame = next;
+          active = my_frame < static_cast<long long>(p.frames);
+          need_init = true;
+        }
       }
     }
     if (!fin) ++it;

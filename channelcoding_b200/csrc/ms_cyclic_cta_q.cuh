@@ -21,7 +21,10 @@
 namespace ccgpu {
 
 // packed messages per thread -> resident CTAs per SM the register allocation aims at
-template <class S> constexpr int ms_cta_q_min_blocks() { return S::RPL * S::W <= 32 ? 8 : S::RPL * S::W <= 72 ? 4 : 2; }
+#ifndef CCGPU_CTA_Q_SMALL_MINBLK
+#define CCGPU_CTA_Q_SMALL_MINBLK 8
+#endif
+template <class S> constexpr int ms_cta_q_min_blocks() { return S::RPL * S::W <= 32 ? CCGPU_CTA_Q_SMALL_MINBLK : S::RPL * S::W <= 72 ? 4 : 2; }
 
 template <class S>
 __global__ void __launch_bounds__(S::THREADS, ms_cta_q_min_blocks<S>()) ms_cyclic_cta_q_kernel(const __grid_constant__ MsParams p) {
@@ -35,6 +38,11 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_q_min_blocks<S>()) ms_cycli
   __shared__ unsigned part[WPF][NPAD];   // per-warp partial column sums
   __shared__ unsigned bword[2][CPASS * WPF];
   __shared__ long long s_next[2];
+  constexpr int NBLK = (N + 3) >> 2;
+  // grouped mode (as in ms_cyclic_cta.cuh): frames are drawn in groups of WPF, one per warp; the quantised channel values
+  // are parked here, all-positive frames are counted by their warp and never reach the decoder
+  __shared__ __align__(8) unsigned short stage16[WPF][4 * NBLK];
+  __shared__ int s_hard[WPF];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int k = S::K > 0 ? S::K : p.k;
   unsigned short *const ybuf16 = reinterpret_cast<unsigned short *>(ybuf);
@@ -77,13 +85,19 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_q_min_blocks<S>()) ms_cycli
     need_init[h] = true;
   }
   const long long units = 2 * static_cast<long long>(gridDim.x);
-  constexpr int NBLK = (N + 3) >> 2;
   for (int c = tid; c < NPAD; c += THREADS) {
     ybuf[c] = 0u;
     sbuf[c] = 0u;
   }
   const unsigned kMmax = p.q_h2_mmax, kAlpha = p.q_h2_alpha, k1024 = p.q_h2_1024, k1024B = p.q_h2_1024b;  // fp16x2, host-made
   const bool quick_ok = p.quick_hint != 0 && p.L == nullptr && p.stop_rule != STOP_NONE && p.max_iter >= 1;
+  const bool grouped = quick_ok && p.src == SRC_PHILOX && p.counters != nullptr && p.bits == nullptr && p.iter == nullptr &&
+                       p.failed == nullptr && p.packed == nullptr && p.status == nullptr;
+  long long grp = blockIdx.x;  // grouped mode: the queue hands out groups of WPF frames
+  int w_next = WPF;            // next staging row to look at; WPF: screen a new group first
+  bool first_group = true, exhausted = false;
+  unsigned quick_frames = 0;   // per warp: frames of this warp decided by the screening
+  if (grouped) active[0] = active[1] = static_cast<long long>(blockIdx.x) * WPF < static_cast<long long>(p.frames);
   __syncthreads();
 
   while (active[0] || active[1]) {
@@ -92,6 +106,74 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_q_min_blocks<S>()) ms_cycli
     while (true) {
       const bool need[2] = { active[0] && need_init[0], active[1] && need_init[1] };  // block-uniform
       if (!need[0] && !need[1]) break;
+      if (grouped) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          if (!need[h]) continue;
+          long long fr = -1;  // the next frame that needs the decoder (block-uniform search)
+          while (!exhausted) {
+            if (w_next >= WPF) {
+              if (!first_group) {
+                if (tid == 0) s_next[0] = static_cast<long long>(gridDim.x) + static_cast<long long>(atomicAdd(p.work, 1ull));
+                __syncthreads();
+                grp = s_next[0];
+              }
+              first_group = false;
+              if (grp * WPF >= static_cast<long long>(p.frames)) {
+                exhausted = true;
+                break;
+              }
+              const long long fw = grp * WPF + warp;
+              bool hard = false;
+              if (fw < static_cast<long long>(p.frames)) {
+                bool pos = true;
+#pragma unroll
+                for (int b0 = 0; b0 < NBLK; b0 += 32) {
+                  const int b = b0 + lane;
+                  if (b < NBLK) {
+                    const float4 v = awgn_block(p.keys, p.point, p.frame0 + static_cast<uint64_t>(fw), b, p.sigma);
+                    const unsigned short q0 = quantise_h(v.x, p.q_scale, p.q_ymax), q1 = quantise_h(v.y, p.q_scale, p.q_ymax),
+                                         q2 = quantise_h(v.z, p.q_scale, p.q_ymax), q3 = quantise_h(v.w, p.q_scale, p.q_ymax);
+                    pos &= static_cast<short>(q0) > 0 && (4 * b + 1 >= N || static_cast<short>(q1) > 0) &&
+                           (4 * b + 2 >= N || static_cast<short>(q2) > 0) && (4 * b + 3 >= N || static_cast<short>(q3) > 0);
+                    *reinterpret_cast<uint2 *>(&stage16[warp][4 * b]) = make_uint2(q0 | (static_cast<unsigned>(q1) << 16), q2 | (static_cast<unsigned>(q3) << 16));
+                  }
+                }
+                hard = !__all_sync(kFull, pos);
+                if (!hard) ++quick_frames;
+              }
+              if (lane == 0) s_hard[warp] = hard ? 1 : 0;
+              __syncthreads();
+              w_next = 0;
+            }
+            while (w_next < WPF && !s_hard[w_next]) ++w_next;
+            if (w_next < WPF) {
+              fr = grp * WPF + w_next;
+              break;
+            }
+          }
+          if (fr < 0) {
+            active[h] = false;
+            continue;
+          }
+          frame[h] = fr;
+          for (int c = tid; c < N; c += THREADS) {
+            const unsigned short v = stage16[w_next][c];
+            ybuf16[2 * c + h] = v;
+            sbuf16[2 * c + h] = v;
+          }
+          ++w_next;
+          const unsigned keep = h == 0 ? 0xffff0000u : 0x0000ffffu;
+#pragma unroll
+          for (int i = 0; i < RPL; ++i)
+#pragma unroll
+            for (int j = 0; j < W; ++j) r[i][j] &= keep;
+          it[h] = 0;
+          need_init[h] = false;
+        }
+        __syncthreads();
+        break;
+      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         if (!need[h]) continue;
@@ -297,7 +379,7 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_q_min_blocks<S>()) ms_cycli
           cnt[C_BIT_ERR] += static_cast<unsigned>(nbits);
           cnt[C_FRAME_ERR] += (failed || nbits != 0) ? 1 : 0;
           cnt[C_UNDETECTED] += (!failed && nbits != 0) ? 1 : 0;
-          s_next[h] = units + static_cast<long long>(atomicAdd(p.work, 1ull));
+          if (!grouped) s_next[h] = units + static_cast<long long>(atomicAdd(p.work, 1ull));
         }
       }
     }
@@ -306,9 +388,11 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_q_min_blocks<S>()) ms_cycli
 #pragma unroll
       for (int h = 0; h < 2; ++h)
         if (fin[h]) {
-          frame[h] = s_next[h];
-          active[h] = frame[h] < static_cast<long long>(p.frames);
-          need_init[h] = true;
+          if (!grouped) {
+            frame[h] = s_next[h];
+            active[h] = frame[h] < static_cast<long long>(p.frames);
+          }
+          need_init[h] = true;  // grouped mode: the refill finds the slot's next frame (or ends the slot)
         }
     }
 #pragma unroll
@@ -320,6 +404,10 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_q_min_blocks<S>()) ms_cycli
   if (tid == 0 && p.counters != nullptr)
     for (int s = 0; s < 6; ++s)
       if (cnt[s]) atomicAdd(p.counters + s, cnt[s]);
+  if (grouped && lane == 0 && quick_frames) {  // iteration 0 decided them: one iteration each, no errors
+    atomicAdd(p.counters + C_FRAMES, static_cast<unsigned long long>(quick_frames));
+    atomicAdd(p.counters + C_ITER, static_cast<unsigned long long>(quick_frames));
+  }
 }
 
 }  // namespace ccgpu

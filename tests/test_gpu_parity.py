@@ -788,6 +788,35 @@ def test_all_positive_shortcut_is_exact(ctx, name, ebno, catalogue):
     assert c0 == c1   # fused Monte-Carlo point: identical counters with and without the shortcut
 
 
+@pytest.mark.parametrize("name", ["bch_31_16", "bch_63_36", "bch_63_45", "bch_127_64", "bch_127_106", "bch_255_131"])
+def test_screening_gives_the_same_counters(ctx, name, catalogue):
+    """Monte-Carlo points with counters only: the QUICK warp kernel screens frames in passes of 32 / NBLK (ms_cyclic.cuh
+    SCREEN), the CTA kernel in groups of four (ms_cyclic_cta.cuh grouped mode); all-positive frames are counted without
+    ever reaching the decoder.  The noise is keyed by the frame index, so the eight counters must equal those of the
+    frame-at-a-time path (option quick = 0) exactly -- at low, medium and very high Eb/N0, for ragged frame counts (1, a
+    few, not a multiple of the pass size), frame offsets, both stop rules and the self-correcting flavour."""
+    e = catalogue[name]
+    code = make_code(ctx, e)
+    big = 200000 if e["n"] < 255 else 40000
+    cases = [(4.0, big // 4, "NMS", 0.8, 0.0, 50, 0, 0), (7.0, big, "NMS", 0.8, 0.0, 50, 0, 5), (10.0, 4 * big + 3, "NMS", 0.8, 0.0, 50, 0, 0),
+             (12.0, 4 * big + 1, "MS", 1.0, 0.0, 50, 1, 123456789012), (8.0, 1, "NMS", 0.8, 0.0, 50, 0, 7), (8.0, 3, "MS", 1.0, 0.0, 50, 0, 0),
+             (8.0, 131, "OMS", 1.0, 0.3, 20, 0, 0), (7.5, big, "SCMS2", 1.0, 0.0, 50, 0, 0), (9.0, big, "2DNMS", 0.9, 0.8, 25, 1, 1),
+             (9.0, big, "NMS", 0.8, 0.0, 1, 0, 0), (5.0, big // 4, "NMS_Q", 0.8, 0.0, 50, 0, 0), (9.0, big, "NMS_Q", 0.8, 0.0, 50, 0, 3),
+             (12.0, 2 * big + 1, "MS_Q", 1.0, 0.0, 50, 1, 0), (10.0, 5, "NMS_Q", 0.8, 0.0, 50, 0, 0)]
+    for ebno, frames, variant, alpha, beta, mi, stop, f0 in cases:
+        res = []
+        for quick in (1, 0):
+            ctx.set_option("quick", quick)
+            try:
+                res.append(code.awgn_point(ebno, frames, variant, alpha, beta, mi, stop, seed=11, point=3, frame0=f0))
+            finally:
+                ctx.set_option("quick", -1)
+        res.append(code.awgn_point(ebno, frames, variant, alpha, beta, mi, stop, seed=11, point=3, frame0=f0))  # the host's own choice
+        what = "%s %s %.1f dB %d frames" % (name, variant, ebno, frames)
+        assert res[0] == res[1] == res[2], (what, res)
+        assert res[0]["frames"] == frames, what
+
+
 def test_every_compiled_shape_keeps_the_reference_order(ctx, catalogue):
     """Guard for the ordered column sums (ms_cyclic.cuh VOLCS: program order through volatile shared-memory accesses
     instead of one __syncwarp per tap -- formally a race under independent thread scheduling, in practice decided by
