@@ -226,9 +226,12 @@ def other_configs(ctx, torch, dist, np, world, rank, dev, timed, args):
     # ---- configs[0]: BCH(15,7) sum-product, Eb/N0 1..6 dB
     c15 = ctx.bch(4, errors=2)
     for eb in (1.0, 3.0, 6.0):
-        point("configs[0] BCH(15,7) t=2 sum-product BP", "ms_cyclic_kernel<bch_15_7, VN_SPA>", c15, eb, 1 << 24, "SPA", 1.0, stop=1,
+        point("configs[0] BCH(15,7) t=2 sum-product BP", "ms_cyclic_lane_kernel<bch_15_7, VN_SPA>", c15, eb, 1 << 24, "SPA", 1.0, stop=1,
               cpu=(4, 2, 0) if eb == 3.0 else None,
               note="the reference has no sum-product decoder: cpu_baseline is its min-sum decoder of the same code")
+    # the same code with the reference's own decoder family (min-sum), the like-for-like line for its CPU baseline
+    point("configs[0] BCH(15,7) t=2 min-sum (the reference's decoder of this code)", "ms_cyclic_lane_kernel<bch_15_7, VN_PLAIN>", c15, 3.0,
+          1 << 25, "MS", 1.0, cpu=(4, 2, 0))
     # ---- configs[2]: BCH(127,64), H(), redundant H (127 cyclic shifts), multiple bases
     c127 = ctx.bch(7, errors=10)
     point("configs[2] BCH(127,64) t=10 NMS on H() (63 rows)", "ms_cyclic_kernel<bch_127_64, VN_PLAIN>", c127, 5.0, 1 << 20, "NMS",
@@ -554,6 +557,8 @@ def main():
         wf_frame = rec.get("smem_wavefronts_per_unit") if (rec and current) else None
         ins_frame = rec.get("warp_instructions_per_unit") if (rec and current) else None
         traffic_frame = rec.get("dram_bytes_per_unit") if (rec and current) else None
+        rec_p, current_p = ncu_capture("K2 ms_cyclic BCH(63,36) NMS 4 dB resident, compact outputs")
+        traffic_packed = rec_p.get("dram_bytes_per_unit") if (rec_p and current_p) else None
         capture_note = ("profiles/r2_kernels.json, csrc_sha %s" % rec.get("csrc_sha")) if (rec and current) else \
                        "no ncu capture of the current sources (csrc_sha %s): per-frame pipe counts withheld" % csrc_hash()
         line = {
@@ -586,6 +591,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak,
                          "traffic": (traffic_frame * B if traffic_frame else None), "capture": capture_note,
+                         # DRAM bytes per frame measured by ncu: `value`'s layout (one byte per decided bit, as the
+                         # reference's correct() returns them) and the compact layout the 264 algorithmic bytes assume
+                         "traffic_bytes_per_frame": traffic_frame, "traffic_bytes_per_frame_compact_outputs": traffic_packed,
                          "peak_source": which, "kernel": "ms_cyclic_kernel<Shape<63,27,...>, VN_PLAIN>",
                          "bytes_per_frame": ALGO_BYTES_PER_FRAME,
                          "note": "the decoder is on-chip ALU/shared-memory bound, not HBM bound: see alu"},

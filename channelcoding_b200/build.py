@@ -33,6 +33,7 @@ def _units():
     units = [("api.o", "api.cu", []), ("ms_registry.o", "ms_registry.cu", []), ("ms_csr.o", "ms_csr.cu", []),
              ("gf_decode.o", "gf_decode.cu", []), ("group.o", "group.cc", [])]
     units.append(("ms_cyclic_cta.o", "ms_cyclic_cta_inst.cu", []))
+    units.append(("ms_cyclic_lane.o", "ms_cyclic_lane_inst.cu", []))
     for g in range(_groups()):
         units.append(("ms_cyclic_g%d.o" % g, "ms_cyclic_inst.cu", ["-DCCGPU_GROUP=%d" % g]))
     return units

@@ -39,6 +39,7 @@ struct ccgpu_ctx {
   // are read ONCE, at ccgpu_create)
   int opt_quick = -1;        // -1: the host's estimate decides (api.cu ccgpu_awgn_point), 0 / 1: force
   int opt_work_batch = 0;    // 0: default
+  int opt_lane = -1;         // lane-per-frame kernel for the small codes (ms_cyclic_lane.cuh): -1 / 1 use it, 0 do not
   // device staging for host-pointer calls (grown on demand)
   void *d_stage = nullptr;
   size_t d_stage_bytes = 0;
@@ -63,6 +64,9 @@ struct ccgpu_code {
   const MsCyclicEntry *cyc[VN_COUNT] = {};
   int grid_max[VN_COUNT] = {};
   size_t smem[VN_COUNT] = {};
+  // lane-per-frame kernels of the small codes (VN_PLAIN, VN_2D, VN_SPA), preferred for HBM / Philox sources
+  const MsCyclicEntry *lane[VN_COUNT] = {};
+  int lane_grid_max[VN_COUNT] = {};
   bool all_columns_covered = false;
   unsigned max_col_weight = 0;
   MsCsrDevice csr;     // general-H kernel tables (device)
@@ -429,6 +433,10 @@ void select_cyclic(ccgpu_code *c) {
     const MsCyclicEntry *e = ms_cyclic_at(i);
     if (e->n != n || e->w != w || !std::equal(c->shape.taps.begin(), c->shape.taps.end(), e->taps)) continue;
     const bool exact = e->k == k && !e->wrap && c->shape.kind == 0;
+    if (e->cta == 2) {
+      if (exact) c->lane[e->vn] = e;
+      continue;
+    }
     const bool redundant = e->k == 0 && e->wrap && k <= (e->cta ? e->threads : 32) * e->rpl;
     if (!exact && !redundant) continue;
     if (c->cyc[e->vn] && !exact) {
@@ -452,6 +460,13 @@ void select_cyclic(ccgpu_code *c) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void *>(c->cyc[vn]->fn),
                                                   c->cyc[vn]->threads, c->smem[vn]);
     c->grid_max[vn] = std::max(1, occ) * c->ctx->sm_count;
+  }
+  for (int vn = 0; vn < VN_COUNT; ++vn) {
+    if (!c->lane[vn]) continue;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, reinterpret_cast<const void *>(c->lane[vn]->fn), c->lane[vn]->threads,
+                                                  size_t(c->lane[vn]->dyn_smem));
+    c->lane_grid_max[vn] = std::max(1, occ) * c->ctx->sm_count;
   }
 }
 
@@ -562,6 +577,24 @@ int launch_ms(ccgpu_ctx *ctx, const ccgpu_code *c, const ccgpu_ms_params *p, MsP
     if (!c->cyc[VN_FIX]) return fail(ctx, CCGPU_ERR_UNSUPPORTED, "fixed-point min-sum runs on the shape-specialised cyclic kernels only");
     const int rc = check_params_q(ctx, c, p);
     if (rc) return rc;
+  }
+  // small codes: one lane per frame (ms_cyclic_lane.cuh) for frames from HBM or the Philox channel; the exhaustive
+  // bit-flip source and the self-correcting flavour stay on the warp kernel
+  if (ctx->opt_lane != 0 && c->lane[vn] && mp.src != SRC_BITFLIP) {
+    const MsCyclicEntry *e = c->lane[vn];
+    const uint64_t want = (mp.frames + e->threads - 1) / e->threads;
+    const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(want, c->lane_grid_max[vn]));
+    CU(cudaMemsetAsync(work, 0, sizeof(unsigned long long), stream));
+    mp.work = work;
+    const uint64_t warps = uint64_t(grid) * (e->threads / 32);
+    unsigned shift = 0;
+    while ((uint64_t(1) << shift) < 4 * warps) ++shift;
+    mp.work_batch = ctx->opt_work_batch > 0 ? static_cast<unsigned>(ctx->opt_work_batch) : 32;
+    mp.work_shift = shift;
+    void *args[] = { &mp };
+    CU(cudaLaunchKernel(reinterpret_cast<const void *>(e->fn), dim3(grid), dim3(e->threads), args, size_t(e->dyn_smem), stream));
+    ctx->launches++;
+    return CCGPU_OK;
   }
   // the QUICK instantiation retires all-positive frames without iterating (ms_cyclic.cuh); it pays when such frames
   // are frequent, i.e. in Monte-Carlo points at high Eb/N0 (the hint is set by ccgpu_awgn_point; CCGPU_QUICK=0/1
@@ -743,6 +776,7 @@ int ccgpu_set_option(ccgpu_ctx *ctx, const char *name, int64_t value) {
   std::lock_guard<std::mutex> g(ctx->mu);
   const std::string n(name);
   if (n == "quick") ctx->opt_quick = value < 0 ? -1 : (value ? 1 : 0);
+  else if (n == "lane") ctx->opt_lane = value < 0 ? -1 : (value ? 1 : 0);
   else if (n == "work_batch") ctx->opt_work_batch = value > 0 ? static_cast<int>(std::min<int64_t>(value, 1024)) : 0;
   else return fail(ctx, CCGPU_ERR_INVALID, "unknown option " + n);
   return CCGPU_OK;

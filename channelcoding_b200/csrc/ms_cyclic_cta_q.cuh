@@ -22,7 +22,8 @@ namespace ccgpu {
 
 // packed messages per thread -> resident CTAs per SM the register allocation aims at
 #ifndef CCGPU_CTA_Q_SMALL_MINBLK
-#define CCGPU_CTA_Q_SMALL_MINBLK 8
+#define CCGPU_CTA_Q_SMALL_MINBLK 6  /* rows of weight <= 32 (the 127-row BCH(127,64)): resident CTAs per SM asked for. \
+   Measured NMS_Q 5 dB: 8 (64 registers, 440 bytes spilled) 2.00e7 frames/s, 7 (72) 2.16e7, 6 (80) 2.24e7 */
 #endif
 template <class S> constexpr int ms_cta_q_min_blocks() { return S::RPL * S::W <= 32 ? CCGPU_CTA_Q_SMALL_MINBLK : S::RPL * S::W <= 72 ? 4 : 2; }
 

@@ -82,7 +82,8 @@ struct MsCyclicEntry {
   const char *name;
   int n, k /* 0: rows at run time */, w, rpl, fpw, np, wrap, vn;
   int threads;  // CTA size
-  int cta;      // 0: ms_cyclic_kernel (warp owns frames), 1: ms_cyclic_cta_kernel (CTA owns one frame)
+  int cta;      // 0: ms_cyclic_kernel (warp owns frames), 1: ms_cyclic_cta_kernel (CTA owns one frame),
+                // 2: ms_cyclic_lane_kernel (lane owns a frame, small codes; kept in ccgpu_code::lane, not ::cyc)
   int slots;    // frames a lane / thread works on at once (2 for the fixed-point kernels, else 1)
   int dyn_smem; // cta == 1: bytes of dynamic shared memory the kernel needs (gather buffer of the float CTA kernel)
   const int *taps;

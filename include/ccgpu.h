@@ -136,7 +136,8 @@ int ccgpu_sync(ccgpu_ctx *ctx);
 uint64_t ccgpu_kernel_launches(const ccgpu_ctx *ctx);
 /* tuning overrides.  "quick": -1 the library decides per call whether frames with all-positive channel values are
  * retired without iterating (same results either way), 0 / 1 force it off / on -- the parity tests drive both paths
- * with it; "work_batch": most frame indices a warp takes from the frame queue per atomic (0 = default).  The
+ * with it; "lane": -1 / 1 the n = 15 codes run on the lane-per-frame kernel, 0 on the general warp kernel (same results;
+ * the tests compare the two); "work_batch": most frame indices a warp takes from the frame queue per atomic (0 = default).  The
  * environment variables CCGPU_QUICK / CCGPU_WORK_BATCH are read once, at ccgpu_create, as initial values. */
 int ccgpu_set_option(ccgpu_ctx *ctx, const char *name, int64_t value);
 /* "nvcc <version> sm_100a abi <n>": the toolkit the kernels were compiled with.  The bit-exactness of the ordered

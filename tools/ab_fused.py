@@ -17,6 +17,7 @@ def main():
     ap.add_argument("--alpha", type=float, default=0.8)
     ap.add_argument("--rows", type=int, default=0)
     ap.add_argument("--quick", type=int, default=-1)
+    ap.add_argument("--lane", type=int, default=-1)
     ap.add_argument("--reps", type=int, default=5)
     a = ap.parse_args()
     import torch
@@ -24,6 +25,7 @@ def main():
     ctx = cc.Context(0)
     ctx.use_torch_stream()
     ctx.set_option("quick", a.quick)
+    ctx.set_option("lane", a.lane)
     code = ctx.bch(a.q, errors=a.t)
     if a.rows:
         code.set_rows(a.rows)
@@ -45,8 +47,8 @@ def main():
         frames = int(min(max(frames * 60.0 / max(ms, 1e-3), 1 << 18), 1 << 31))
         best = min(run(frames) for _ in range(a.reps))
         c = cnt.cpu().numpy()
-        print("%s quick=%d (%d,%d) rows=%d %s %5.1f dB: %.4e frames/s  (%d frames, %.2f ms)  wer %.3e it %.4f  counters %s" % (
-            lib, a.quick, code.n, code.l, code.h_rows, a.variant, eb, frames / best * 1e3, frames, best, c[1] / c[0], c[3] / c[0],
+        print("%s quick=%d lane=%d (%d,%d) rows=%d %s %5.1f dB: %.4e frames/s  (%d frames, %.2f ms)  wer %.3e it %.4f  counters %s" % (
+            lib, a.quick, a.lane, code.n, code.l, code.h_rows, a.variant, eb, frames / best * 1e3, frames, best, c[1] / c[0], c[3] / c[0],
             " ".join(str(int(x)) for x in c[:6])), flush=True)
 
 

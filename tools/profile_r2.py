@@ -30,7 +30,7 @@ def main():
         torch.cuda.synchronize()
         return e0.elapsed_time(e1)
 
-    def decode_target(label, match, code, eb, frames, variant, alpha=0.8, quant=None, quick=-1):
+    def decode_target(label, match, code, eb, frames, variant, alpha=0.8, quant=None, quick=-1, packed=False):
         y = torch.empty((frames, code.n), dtype=torch.float32, device="cuda")
         ctx.awgn_llr(code.n, np.float32(cc.sigma(code.rate, eb)), 0, 1, 0, frames, out=y)
         manifest.append({"label": "K1 awgn_llr n=%d (input of %s)" % (code.n, label), "match": "awgn_llr_kernel", "units": frames,
@@ -38,9 +38,14 @@ def main():
         out = (torch.empty((frames, code.n), dtype=torch.uint8, device="cuda"), None,
                torch.empty(frames, dtype=torch.uint8, device="cuda"), torch.empty(frames, dtype=torch.uint8, device="cuda"))
         ctx.set_option("quick", quick)
-        ms = ev(lambda: code.decode(y, variant, alpha, 0.0, 50, out=out, want_L=False, quant=quant))
+        if packed:  # compact output layout: the 264 algorithmic bytes per frame of SURVEY 8(d)
+            pk = (torch.empty((frames, (code.n + 31) // 32), dtype=torch.int32, device="cuda"), torch.empty(frames, dtype=torch.uint8, device="cuda"))
+            ms = ev(lambda: code.decode_packed(y, variant, alpha, 0.0, 50, out=pk, quant=quant))
+            it = torch.where(pk[1] == 255, torch.full_like(pk[1], 50).int(), pk[1].int() + 1).double().mean().item()
+        else:
+            ms = ev(lambda: code.decode(y, variant, alpha, 0.0, 50, out=out, want_L=False, quant=quant))
+            it = torch.where(out[3] == 1, torch.full_like(out[2], 50).int(), out[2].int() + 1).double().mean().item()
         ctx.set_option("quick", -1)
-        it = torch.where(out[3] == 1, torch.full_like(out[2], 50).int(), out[2].int() + 1).double().mean().item()
         manifest.append({"label": label, "match": match, "units": frames, "unit": "frame", "avg_iterations": it,
                          "edges": code.edges, "bytes_per_unit": 4 * code.n + 4 * ((code.n + 31) // 32) + 4, "ms_no_ncu": ms})
         print("%-46s %8.3f ms  %.3e frames/s  %.2f it" % (label, ms, frames / ms * 1e3, it))
@@ -58,26 +63,33 @@ def main():
     c63 = ctx.bch(6, errors=5)
     M = 1 << 20
     decode_target("K2 ms_cyclic BCH(63,36) NMS 4 dB resident", "ms_cyclic_kernel", c63, 4.0, M, "NMS")
+    decode_target("K2 ms_cyclic BCH(63,36) NMS 4 dB resident, compact outputs", "ms_cyclic_kernel", c63, 4.0, M, "NMS", packed=True)
     decode_target("K2q ms_cyclic_q BCH(63,36) NMS_Q 4 dB resident", "ms_cyclic_q_kernel", c63, 4.0, M, "NMS_Q", quant=(8.0, 31, 31))
     point_target("K2 ms_cyclic BCH(63,36) NMS 4 dB fused", "ms_cyclic_kernel", c63, 4.0, M, "NMS")
     point_target("K2q ms_cyclic_q BCH(63,36) NMS_Q 4 dB fused", "ms_cyclic_q_kernel", c63, 4.0, M, "NMS_Q", quant=(8.0, 31, 31))
     point_target("K2 QUICK BCH(63,36) NMS 7 dB fused", "ms_cyclic_kernel", c63, 7.0, 4 * M, "NMS", quick=1)
+    point_target("K2 QUICK screening BCH(63,36) NMS 10 dB fused", "ms_cyclic_kernel", c63, 10.0, 32 * M, "NMS", quick=1)
     point_target("K2q skip BCH(63,36) NMS_Q 8 dB fused", "ms_cyclic_q_kernel", c63, 8.0, 4 * M, "NMS_Q", quant=(8.0, 31, 31), quick=1)
     point_target("K2 SC BCH(63,36) SCMS2 4 dB fused", "ms_cyclic_kernel", c63, 4.0, M, "SCMS2", 1.0)
     c15 = ctx.bch(4, errors=2)
-    point_target("K2 SPA BCH(15,7) sum-product 3 dB fused", "ms_cyclic_kernel", c15, 3.0, 4 * M, "SPA", 1.0, stop=1)
-    point_target("K2 ms_cyclic BCH(15,7) MS 3 dB fused", "ms_cyclic_kernel", c15, 3.0, 8 * M, "MS", 1.0)
+    point_target("K2s ms_cyclic_lane BCH(15,7) sum-product 3 dB fused", "ms_cyclic_lane_kernel", c15, 3.0, 4 * M, "SPA", 1.0, stop=1)
+    point_target("K2s ms_cyclic_lane BCH(15,7) MS 3 dB fused", "ms_cyclic_lane_kernel", c15, 3.0, 16 * M, "MS", 1.0)
+    ctx.set_option("lane", 0)
+    point_target("K2 ms_cyclic BCH(15,7) MS 3 dB fused (warp kernel, option lane = 0)", "ms_cyclic_kernel", c15, 3.0, 8 * M, "MS", 1.0)
+    ctx.set_option("lane", -1)
     c127 = ctx.bch(7, errors=10)
     point_target("K2 ms_cyclic BCH(127,64) NMS 5 dB fused", "ms_cyclic_kernel", c127, 5.0, M // 4, "NMS")
     point_target("K2q ms_cyclic_q BCH(127,64) NMS_Q 5 dB fused", "ms_cyclic_q_kernel", c127, 5.0, M // 4, "NMS_Q", quant=(8.0, 31, 31))
     c127.set_rows(127)
-    point_target("K2 ms_cyclic BCH(127,64) 127-row H NMS 5 dB", "ms_cyclic_kernel", c127, 5.0, M // 8, "NMS")
+    point_target("K2c ms_cyclic_cta BCH(127,64) 127-row H NMS 5 dB", "ms_cyclic_cta_kernel", c127, 5.0, M // 8, "NMS")
     point_target("K2cq ms_cyclic_cta_q BCH(127,64) 127-row H NMS_Q 5 dB", "ms_cyclic_cta_q_kernel", c127, 5.0, M // 8, "NMS_Q",
                  quant=(8.0, 31, 31))
     c255 = ctx.bch(8, errors=18)
     point_target("K2c ms_cyclic_cta BCH(255,131) NMS 6 dB fused", "ms_cyclic_cta_kernel", c255, 6.0, M // 8, "NMS")
     point_target("K2cq ms_cyclic_cta_q BCH(255,131) NMS_Q 6 dB fused", "ms_cyclic_cta_q_kernel", c255, 6.0, M // 8, "NMS_Q",
                  quant=(8.0, 31, 29))
+    point_target("K2c grouped BCH(255,131) NMS 11.5 dB fused", "ms_cyclic_cta_kernel", c255, 11.5, 16 * M, "NMS")
+    point_target("K2cq grouped BCH(255,131) NMS_Q 11.5 dB fused", "ms_cyclic_cta_q_kernel", c255, 11.5, 16 * M, "NMS_Q", quant=(8.0, 31, 29))
     # K2g: the (63,45) checks in a non-cyclic row order -> CSR kernel
     c45 = ctx.bch(6, dmin=7)
     g = ctx.from_dense(c45.H()[np.random.default_rng(1).permutation(c45.h_rows)], c45.rate)
