@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(256) count_words_kernel(const uint8_t *__restr
 // H: same n, same tap offsets, and either the same number of rows without wrap-around or a
 // redundant (run-time rows, wrap-around) shape.  Nothing fits -> CSR kernel.
 void select_cyclic(ccgpu_code *c) {
-  for (int vn = 0; vn < VN_COUNT; ++vn) c->cyc[vn] = nullptr;
+  for (int vn = 0; vn < VN_COUNT; ++vn) c->cyc[vn] = c->lane[vn] = nullptr;
   if (c->shape.kind > 1 || c->shape.taps.empty()) return;
   const int n = static_cast<int>(c->spec.n), k = static_cast<int>(c->spec.rows);
   const int w = static_cast<int>(c->shape.taps.size());

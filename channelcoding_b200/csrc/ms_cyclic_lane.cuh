@@ -76,6 +76,11 @@ __global__ void __launch_bounds__(kMsThreads, CCGPU_MS_LANE_MINBLK) ms_cyclic_la
 #pragma unroll
     for (int j = 0; j < W; ++j) r[i][j] = 0.0f;
 
+  const bool is_oms = p.variant == V_OMS;
+  const float fn_scale = (p.variant == V_NMS || p.variant == V_NMS2D) ? p.alpha_f : 1.0f;
+  const unsigned ov_mask = p.stop_rule == STOP_REF ? 255u : (p.stop_rule == STOP_GF2 ? 1u : 0u);
+  const unsigned ov_none = p.stop_rule == STOP_NONE ? 1u : 0u;  // no stop rule: never "converged"
+
   while (true) {
     // ================= lanes without a frame take the next ones of the FIFO
     const unsigned needm = __ballot_sync(kFull, !active);
@@ -206,7 +211,11 @@ __global__ void __launch_bounds__(kMsThreads, CCGPU_MS_LANE_MINBLK) ms_cyclic_la
           m1 = fminf(m1, a);
           par ^= __float_as_uint(q[j]);
         }
-        const float2 g = cn_magnitude_pair(p, m1, m2);  // fn_h of the variant (:204-213, :245-251)
+        // fn_h of the variant (:204-213, :245-251).  m1 / m2 are never NaN (fminf keeps the other operand), so the
+        // unnormalised variants can multiply by 1.0f exactly instead of branching per row; the offset rule (double
+        // intermediate) is the rare, warp-uniform case
+        float2 g = make_float2(__fmul_rn(fn_scale, m1), __fmul_rn(fn_scale, m2));
+        if (is_oms) g = cn_offset_pair(p.beta_d, m1, m2);
         const float f1 = xor_sign(g.x, par), f2 = xor_sign(g.y, par);
 #pragma unroll
         for (int j = 0; j < W; ++j) {
@@ -230,18 +239,16 @@ __global__ void __launch_bounds__(kMsThreads, CCGPU_MS_LANE_MINBLK) ms_cyclic_la
     if (p.stop_simple) {
       stop = word == 0u;
     } else {
-      bool bad = false;
+      // integer overlap of every row with the decided word: reference rule (ov mod 256 != 0), GF(2) parity, or no rule
+      unsigned bad = ov_none;
 #pragma unroll
       for (int i = 0; i < K; ++i) {
         unsigned rm = 0;
 #pragma unroll
         for (int j = 0; j < W; ++j) rm |= 1u << (i + T::get(j));
-        const int ov = __popc(word & rm);
-        if (p.stop_rule == STOP_REF) bad |= (ov & 255) != 0;
-        else if (p.stop_rule == STOP_GF2) bad |= (ov & 1) != 0;
-        else bad = true;
+        bad |= static_cast<unsigned>(__popc(word & rm)) & ov_mask;
       }
-      stop = !bad;
+      stop = bad == 0u;
     }
     const bool fin = active && (stop || it + 1 >= p.max_iter);
     if (fin) {
