@@ -61,6 +61,13 @@
 #ifndef CCGPU_MS_CN_PAIR
 #define CCGPU_MS_CN_PAIR 1
 #endif
+#ifndef CCGPU_MS_UNIFORM
+#define CCGPU_MS_UNIFORM 1  /* see UNI in the kernel: BCH(63,36) NMS 4 dB 2.303e8 -> 2.343e8 frames/s, 6 dB fused +7 %, (63,45) +3.6 % */
+#endif
+#ifndef CCGPU_MS_FNSCALE
+#define CCGPU_MS_FNSCALE 1
+#endif
+
 #ifndef CCGPU_MS_VOLATILE_COLSUM
 #define CCGPU_MS_VOLATILE_COLSUM 1  /* see VOLCS in the kernel */
 #endif
@@ -166,6 +173,12 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VNQ>()) ms_cyclic
   constexpr int VN = QUICK ? VNQ - VN_QUICK : VNQ;
   constexpr int N = S::N, W = S::W, RPL = S::RPL, NP = S::NP, FPW = S::FPW;
   constexpr bool WRAP = S::WRAP, SC = VN == VN_SC, SPA = VN == VN_SPA;
+  // one frame per warp: the schedule state (active, need_init, the iteration counter, the stop decision) is identical in
+  // every lane by construction, so "does any lane ..." needs no vote
+  constexpr bool UNI = CCGPU_MS_UNIFORM && FPW == 1;
+  // fn_h as one multiply per minimum (see the check-node pass): measured BCH(63,36) NMS +1.0 %, MS +1.9 %, OMS +1.8 %, but
+  // -0.4 .. -1.1 % on BCH(127,64) / (63,45) / (31,16): only the small one-frame-per-warp shapes use it
+  constexpr bool FNS = CCGPU_MS_FNSCALE && FPW == 1 && RPL * W <= 18;
   // y of a row's edges is loop invariant: the first YN of them stay in registers (one shared-memory load less per
   // edge and iteration) as far as the 64-register budget of 8 resident CTAs per SM allows
   constexpr int YCAP = CCGPU_MS_YREG_BUDGET - W;
@@ -347,12 +360,16 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VNQ>()) ms_cyclic
   unsigned hardmask = 0;   // staged frames that still need the decoder
   bool first_pass = true;  // the first staged frame of a warp is its statically assigned one
 
+#if CCGPU_MS_FNSCALE
+  const bool is_oms = p.variant == V_OMS;
+  const float fn_scale = (p.variant == V_NMS || p.variant == V_NMS2D) ? p.alpha_f : 1.0f;
+#endif
   while (true) {
-    if (__ballot_sync(kFull, active) == 0u) break;
+    if (UNI ? !active : (__ballot_sync(kFull, active) == 0u)) break;
     bool skip = false;
 
     // ============ (re)fill frame groups that finished
-    const unsigned initm = __ballot_sync(kFull, active && need_init);
+    const unsigned initm = UNI ? ((active && need_init) ? kFull : 0u) : __ballot_sync(kFull, active && need_init);
     if (SCREEN && screen_on) {
       if (active && need_init) {  // warp-uniform: one frame per warp
         __syncwarp();
@@ -614,7 +631,18 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VNQ>()) ms_cyclic
         par ^= __float_as_uint(q);
       }
       m1v[i] = m1;
-#if CCGPU_MS_CN_PAIR
+#if CCGPU_MS_FNSCALE
+      // (compiled in for every shape, used where measured faster: FNS)
+      // fn_h as one multiply per minimum: m1 / m2 are never NaN (fminf keeps the other operand), so x 1.0f is exact for
+      // the unnormalised variants; the offset rule (double intermediate) is a rare warp-uniform call
+      float2 g;
+      if (FNS) {
+        g = make_float2(__fmul_rn(fn_scale, m1), __fmul_rn(fn_scale, m2));
+        if (is_oms) g = cn_offset_pair(p.beta_d, m1, m2);
+      } else {
+        g = cn_magnitude_pair(p, m1, m2);
+      }
+#elif CCGPU_MS_CN_PAIR
       const float2 g = cn_magnitude_pair(p, m1, m2);
 #else
       const float2 g = make_float2(cn_magnitude(p, m1), cn_magnitude(p, m2));
@@ -699,7 +727,7 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VNQ>()) ms_cyclic
     }  // !(QUICK && skip)
     const bool last = it + 1 >= p.max_iter;
     const bool fin = active && (stop || last);
-    const unsigned finm = __ballot_sync(kFull, fin);
+    const unsigned finm = UNI ? (fin ? kFull : 0u) : __ballot_sync(kFull, fin);
     if (finm) {
       // ---- decided word / totals of the finishing groups
       if (p.bits != nullptr || p.L != nullptr) {

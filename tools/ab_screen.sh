@@ -1,9 +1,13 @@
 set -x
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_lane.py -x -q -m gpu 2>&1 | tail -5
-( python tools/ab_fused.py --q 4 --t 2 --ebno 1 3 6 9 --variant MS --alpha 1.0
-python tools/ab_fused.py --q 4 --t 2 --ebno 1 3 6 --variant NMS
-python tools/ab_fused.py --q 4 --t 2 --ebno 3 --variant OMS --alpha 1.0
-python tools/ab_fused.py --q 4 --t 3 --ebno 1 3 6
-) 2>&1 | tee gpurun_out/ab_lane2.txt
-python -m pytest tests -x -q -m gpu 2>&1 | tail -5
+( for rep in 1 2; do for L in libccgpu.so libccgpu_ycol.so libccgpu_y30.so libccgpu_y32.so libccgpu_ycol30.so; do
+  export CCGPU_LIB=$PWD/channelcoding_b200/$L
+  python tools/ab_ms.py --q 6 --t 5 --ebno 4 --frames 4194304
+done; done
+for L in libccgpu.so libccgpu_ycol.so libccgpu_y30.so libccgpu_y32.so libccgpu_ycol30.so; do
+  export CCGPU_LIB=$PWD/channelcoding_b200/$L
+  python tools/ab_ms.py --q 6 --t 3 --ebno 4 --frames 4194304
+  python tools/ab_ms.py --q 6 --t 4 --ebno 4 --frames 4194304
+  python tools/ab_ms.py --q 5 --t 4 --ebno 4 --frames 8388608
+  python tools/ab_ms.py --q 6 --t 5 --ebno 7 --frames 8388608
+done ) 2>&1 | grep -v "^+" | tee gpurun_out/ab_ycol.txt
