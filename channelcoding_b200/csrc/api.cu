@@ -153,17 +153,13 @@ __global__ void __launch_bounds__(kAwgnThreads) awgn_llr_kernel(const __grid_con
       const uint32_t blk = b - f * nblk;
       const float4 v = awgn_block(p.keys, p.point, p.frame0 + f0 + f, blk, p.sigma);
       float *dst = tile + f * n + 4 * blk;
-      if (blk + 1 < nblk) {
-        dst[0] = v.x;
-        dst[1] = v.y;
-        dst[2] = v.z;
-        dst[3] = v.w;
-      } else {  // last block of the frame: n is not a multiple of four
-        const float vv[4] = { v.x, v.y, v.z, v.w };
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (4 * blk + e < n) dst[e] = vv[e];
-      }
+      // branch-free: a separate path for the last block of a frame (n is not a multiple of four) made every warp run
+      // both paths, since every warp holds a last block
+      const uint32_t left = n - 4 * blk;  // >= 1
+      dst[0] = v.x;
+      if (left > 1) dst[1] = v.y;
+      if (left > 2) dst[2] = v.z;
+      if (left > 3) dst[3] = v.w;
     }
     __syncthreads();
     const uint64_t base = f0 * n;              // multiple of 4 floats because tile_frames % 4 == 0

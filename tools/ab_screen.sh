@@ -1,13 +1,7 @@
 set -x
 mkdir -p gpurun_out
-( for rep in 1 2; do for L in libccgpu.so libccgpu_ycol.so libccgpu_y30.so libccgpu_y32.so libccgpu_ycol30.so; do
-  export CCGPU_LIB=$PWD/channelcoding_b200/$L
-  python tools/ab_ms.py --q 6 --t 5 --ebno 4 --frames 4194304
-done; done
-for L in libccgpu.so libccgpu_ycol.so libccgpu_y30.so libccgpu_y32.so libccgpu_ycol30.so; do
-  export CCGPU_LIB=$PWD/channelcoding_b200/$L
-  python tools/ab_ms.py --q 6 --t 3 --ebno 4 --frames 4194304
-  python tools/ab_ms.py --q 6 --t 4 --ebno 4 --frames 4194304
-  python tools/ab_ms.py --q 5 --t 4 --ebno 4 --frames 8388608
-  python tools/ab_ms.py --q 6 --t 5 --ebno 7 --frames 8388608
-done ) 2>&1 | grep -v "^+" | tee gpurun_out/ab_ycol.txt
+( CCGPU_LIB=$PWD/channelcoding_b200/libccgpu_base.so python tools/ab_k1.py
+python tools/ab_k1.py ) 2>&1 | grep -v "^+" | tee gpurun_out/ab_k1.txt
+python tools/sweep.py --q 8 --t 18 --variant NMS --alpha 0.8 --ebno-from 0 --ebno-to 11.5 --ebno-step 0.5 --max-frames 1e10 > gpurun_out/waterfall_255_131_n1_r2b.jsonl 2> gpurun_out/waterfall_r2b.err
+tail -4 gpurun_out/waterfall_255_131_n1_r2b.jsonl | cut -c1-330
+python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "channel" 2>&1 | tail -3
