@@ -369,6 +369,13 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    # stdout carries exactly ONE line, the JSON record.  Native libraries write to file descriptor 1 behind Python's
+    # back (NCCL prints its version banner there whatever NCCL_DEBUG_FILE says): keep a private handle on the real
+    # stdout for the record and point descriptor 1 at stderr for everything else.  The log LEVEL (NCCL_DEBUG) stays the
+    # caller's -- the driver counts the ranks from that log, which now arrives on stderr in full.
+    sys.stdout.flush()
+    record_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
 
     import numpy as np
     import torch
@@ -620,7 +627,8 @@ def main():
                                     "sample": "%.0f s wall on %d threads = %d frames of the same workload "
                                               "(simulation.c++ inner loop incl. noise generation), WER %.4f"
                                               % (args.cpu_seconds, cores, frames, werr / max(1, frames))}
-        print(json.dumps(line))
+        record_out.write(json.dumps(line) + "\n")
+        record_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
