@@ -607,7 +607,7 @@ def main():
             "alu": {"model": "avg_iters*(11E+2n) lane-ops/frame (SURVEY 8d)", "lane_ops_per_frame": lane_ops,
                     "achieved_lane_ops_per_s": value / world * lane_ops, "peak_lane_ops_per_s": alu_peak,
                     "frac": value / world * lane_ops / alu_peak},
-            # the pipes that actually bind (ncu, profiles/r1_ms_cyclic_63_36.txt: issue 79 %, ALU 79 %, LSU 80 %):
+            # the pipes that actually bind (ncu, profiles/r2_kernels.txt: issue 80 %, ALU 77 %, LSU 81 %):
             # shared-memory wavefronts against one per SM per cycle, warp instructions against four per SM per cycle;
             # the per-frame counts come from the committed ncu capture of this kernel at the same Eb/N0
             "smem": {"wavefronts_per_frame": wf_frame, "peak_wavefronts_per_s": 148 * sm_max * 1e6,

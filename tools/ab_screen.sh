@@ -1,7 +1,9 @@
 set -x
 mkdir -p gpurun_out
-( CCGPU_LIB=$PWD/channelcoding_b200/libccgpu_base.so python tools/ab_k1.py
-python tools/ab_k1.py ) 2>&1 | grep -v "^+" | tee gpurun_out/ab_k1.txt
-python tools/sweep.py --q 8 --t 18 --variant NMS --alpha 0.8 --ebno-from 0 --ebno-to 11.5 --ebno-step 0.5 --max-frames 1e10 > gpurun_out/waterfall_255_131_n1_r2b.jsonl 2> gpurun_out/waterfall_r2b.err
-tail -4 gpurun_out/waterfall_255_131_n1_r2b.jsonl | cut -c1-330
-python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "channel" 2>&1 | tail -3
+env | grep -i nccl
+( for L in libccgpu.so libccgpu_lmb3.so libccgpu_lmb5.so; do
+  export CCGPU_LIB=$PWD/channelcoding_b200/$L
+  python tools/ab_fused.py --q 4 --t 2 --ebno 1 3 6 --variant MS --alpha 1.0
+  python tools/ab_fused.py --q 4 --t 2 --ebno 1 3 --variant SPA --alpha 1.0
+  python tools/ab_fused.py --q 4 --t 3 --ebno 3
+done ) 2>&1 | grep -v "^+" | tee gpurun_out/ab_lmb.txt
