@@ -1,5 +1,5 @@
-// ms_cyclic_lane.cuh -- K2s: flooding min-sum / sum-product for SMALL cyclic parity-check matrices (n = 15), sm_100a:
-// one LANE owns one frame.
+// ms_cyclic_lane.cuh -- K2s: flooding min-sum / sum-product for SMALL cyclic parity-check matrices (n = 15, n = 31),
+// sm_100a: one LANE owns one frame.
 //
 // Same arithmetic, same order, same outputs as ms_cyclic_kernel (reference codes/soft_decision.h:161-202:
 // vertical__ :125-140, horizontal__ :101-122, column_sum :86-98 rows ascending, syndrome :79-84); what changes is the
@@ -14,6 +14,10 @@
 //   * the FIFO is filled by the whole warp: Philox blocks, one per lane (8 frames of n = 15 per pass: all lanes busy), or
 //     coalesced loads of up to 32 consecutive frames from HBM.
 //   * frame indices come from the global queue head in batches (one atomic per up to 8 x work_batch frames).
+// n = 31 (80 .. 120 messages + 93 column values per lane): 255 registers with 120 .. 300 bytes of spills, two CTAs per SM --
+// eight warps per SM, but the iteration needs no shared memory and has 5 .. 20 independent rows to overlap: measured
+// 1.3 .. 4.0 x the warp kernel for the min-sum flavours (BCH(31,26) 4 dB 8.0e8 -> 3.2e9 frames/s), 0.9 x for sum-product,
+// which therefore stays on the warp kernel for n = 31 (CCGPU_MS_LANE_SPA_LIST).
 // Float semantics as in ms_cyclic.cuh: explicit _rn adds / multiplies (no contraction), OMS offset in double, the column
 // sums start at +0.0f and add the rows in ascending order (the unrolled row loop IS that order).
 #pragma once
@@ -33,15 +37,17 @@
 namespace ccgpu {
 
 constexpr int kLaneFifo = 64;  // frames a warp's FIFO holds (a power of two >= 32 + the largest producer pass)
-constexpr int kLanePad = 16;   // floats per FIFO slot (n <= 16)
+template <class S> constexpr int ms_lane_pad() { return S::N <= 16 ? 16 : 32; }  // floats per FIFO slot
 template <class S> constexpr int ms_lane_smem_bytes() {
-  return (kMsThreads / 32) * (kLaneFifo * kLanePad * static_cast<int>(sizeof(float)) + kLaneFifo * static_cast<int>(sizeof(long long)));
+  return (kMsThreads / 32) * (kLaneFifo * ms_lane_pad<S>() * static_cast<int>(sizeof(float)) + kLaneFifo * static_cast<int>(sizeof(long long)));
 }
+template <class S> constexpr int ms_lane_min_blocks() { return S::K * S::W <= 48 ? CCGPU_MS_LANE_MINBLK : 2; }
 
 template <class S, int VN>
-__global__ void __launch_bounds__(kMsThreads, CCGPU_MS_LANE_MINBLK) ms_cyclic_lane_kernel(const __grid_constant__ MsParams p) {
+__global__ void __launch_bounds__(kMsThreads, ms_lane_min_blocks<S>()) ms_cyclic_lane_kernel(const __grid_constant__ MsParams p) {
   constexpr int N = S::N, K = S::K, W = S::W;
   constexpr bool SPA = VN == VN_SPA;
+  constexpr int kLanePad = S::N <= 16 ? 16 : 32;  // = ms_lane_pad<S>()
   static_assert(K > 0 && !S::WRAP && N <= kLanePad, "exact small shapes only");
   static_assert(VN == VN_PLAIN || VN == VN_2D || VN == VN_SPA, "flavours of the lane kernel");
   using T = typename S::taps;

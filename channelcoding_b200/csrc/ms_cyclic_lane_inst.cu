@@ -1,5 +1,5 @@
 // ms_cyclic_lane_inst.cu -- instantiates ms_cyclic_lane_kernel (one lane per frame) for the shapes of CCGPU_MS_LANE_LIST
-// (ms_shapes_generated.h): plain (MS / NMS / OMS), two-dimensional and sum-product flavours.
+// (ms_shapes_generated.h): plain (MS / NMS / OMS) and two-dimensional flavours, sum-product for CCGPU_MS_LANE_SPA_LIST.
 #include "ms_cyclic_lane.cuh"
 #include "ms_shapes_generated.h"
 
@@ -19,10 +19,11 @@ template <class S, int VN> MsCyclicEntry make_lane_entry(const char *name) {
                         reinterpret_cast<ms_kernel_fn>(&ms_cyclic_lane_kernel<S, VN>) };
 }
 
-#define X(NAME) make_lane_entry<shapes::NAME, VN_PLAIN>(#NAME), make_lane_entry<shapes::NAME, VN_2D>(#NAME), \
-                make_lane_entry<shapes::NAME, VN_SPA>(#NAME),
-static const MsCyclicEntry kLaneEntries[] = { CCGPU_MS_LANE_LIST(X) };
+#define X(NAME) make_lane_entry<shapes::NAME, VN_PLAIN>(#NAME), make_lane_entry<shapes::NAME, VN_2D>(#NAME),
+#define Y(NAME) make_lane_entry<shapes::NAME, VN_SPA>(#NAME),
+static const MsCyclicEntry kLaneEntries[] = { CCGPU_MS_LANE_LIST(X) CCGPU_MS_LANE_SPA_LIST(Y) };
 #undef X
+#undef Y
 
 const MsCyclicEntry *ms_cyclic_group_lane(int *count) {
   *count = static_cast<int>(sizeof(kLaneEntries) / sizeof(kLaneEntries[0]));

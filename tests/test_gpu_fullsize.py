@@ -101,3 +101,53 @@ def test_bch_15_7_sweep_monotone(ctx):
         assert 0.8 * wer < wer_spa < 1.3 * wer + 1e-5, (eb, wer_spa, wer)
         prev["MS"], prev["SPA"] = wer, wer_spa
     assert prev["MS"] < 1e-3 and prev["SPA"] < 1e-3
+
+
+def test_bch_15_7_full_size_on_the_lane_kernel(ctx):
+    """config[0] at full size on the lane-per-frame kernel: 2e8 frames per point.  Shard-sum linearity of every counter
+    (what 8 GPUs do), equality with the warp kernel on a 2e7-frame slice, and the word error rate inside the 99.9 %
+    interval of the reference's own CPU simulation (tests/golden/ref_wer.json, 1e5 frames per point)."""
+    import json
+    import os
+    code = ctx.bch(4, errors=2)
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_wer.json")) as f:
+        golden = json.load(f)
+    total = 200_000_000
+    for point, eb in enumerate((1.0, 3.0, 5.0)):
+        whole = code.awgn_point(eb, total, "MS", seed=5, point=point)
+        assert whole["frames"] == total and whole["failures"] <= whole["frame_errors"] <= whole["bit_errors"]
+        assert whole["frames"] <= whole["iterations"] <= 50 * total
+        parts = [code.awgn_point(eb, total // 8, "MS", seed=5, point=point, frame0=i * (total // 8)) for i in range(8)]
+        for k in whole:
+            assert sum(p[k] for p in parts) == whole[k], (eb, k)
+        ctx.set_option("lane", 0)
+        try:
+            warp = code.awgn_point(eb, total // 10, "MS", seed=5, point=point, frame0=3 * (total // 10))
+        finally:
+            ctx.set_option("lane", -1)
+        assert warp == code.awgn_point(eb, total // 10, "MS", seed=5, point=point, frame0=3 * (total // 10)), eb
+        ref = [r for r in golden["points"] if r["code"] == "bch_15_7" and abs(r["ebno_db"] - eb) < 1e-9 and r["variant"] == "MS"]
+        if ref:
+            p1, n2 = whole["frame_errors"] / total, ref[0]["frames"]
+            p2 = ref[0]["word_errors"] / n2
+            assert abs(p1 - p2) < 3.3 * math.sqrt(p1 * (1 - p1) / total + p2 * (1 - p2) / n2 + 1e-12), (eb, p1, p2)
+
+
+def test_bch_63_36_error_floor_with_screening(ctx):
+    """config[1] towards the error floor: 2e9 frames at 10 dB (98 % of them are counted by the screening without reaching
+    the decoder).  Every shard accounts for all its frames, the counters add up, one iteration per clean frame."""
+    code = ctx.bch(6, errors=5)
+    shard = 250_000_000
+    shards = [code.awgn_point(10.0, shard, "NMS", 0.8, seed=9, point=20, frame0=i * shard) for i in range(8)]
+    frames = sum(s["frames"] for s in shards)
+    assert frames == 8 * shard and all(s["frames"] == shard for s in shards)
+    ferr = sum(s["frame_errors"] for s in shards)
+    assert ferr / frames < 2e-7 and all(s["failures"] <= s["frame_errors"] <= s["bit_errors"] for s in shards)
+    it = sum(s["iterations"] for s in shards) / frames
+    assert 1.0 <= it < 1.002
+    ctx.set_option("quick", 0)
+    try:
+        plain = code.awgn_point(10.0, 20_000_000, "NMS", 0.8, seed=9, point=20, frame0=3 * shard)
+    finally:
+        ctx.set_option("quick", -1)
+    assert plain == code.awgn_point(10.0, 20_000_000, "NMS", 0.8, seed=9, point=20, frame0=3 * shard)

@@ -1,4 +1,4 @@
-"""GPU parity tests of the lane-per-frame kernel (csrc/ms_cyclic_lane.cuh, the n = 15 codes): bit-exact against the
+"""GPU parity tests of the lane-per-frame kernel (csrc/ms_cyclic_lane.cuh, the n = 15 and n = 31 codes): bit-exact against the
 oracle (pinned to the reference) and against the warp kernel it replaces (option "lane" = 0), through the C ABI."""
 import zlib
 
@@ -10,7 +10,7 @@ from conftest import golden_H, load_golden, VARIANT_PARAMS
 
 pytestmark = pytest.mark.gpu
 
-NAMES = ["bch_15_7", "bch_15_5", "bch_15_7_dmin5", "bch_15_7_dmin6"]
+NAMES = ["bch_15_7", "bch_15_5", "bch_15_7_dmin5", "bch_15_7_dmin6", "bch_31_16", "bch_31_26", "bch_31_21", "bch_31_11"]
 
 
 @pytest.fixture(scope="module")
@@ -91,7 +91,7 @@ def test_lane_kernel_golden(ctx, catalogue, golden_codes):
     assert ctx.kernel_launches > before
 
 
-@pytest.mark.parametrize("name", NAMES[:2])
+@pytest.mark.parametrize("name", ["bch_15_7", "bch_15_5", "bch_31_16", "bch_31_26"])
 def test_lane_kernel_compact_outputs_and_counters(ctx, name, catalogue):
     """compact output layout, and the fused Monte-Carlo point: identical counters on the lane kernel and the warp kernel
     (the noise is keyed by the frame index), for ragged frame counts and frame offsets; sum-product included"""

@@ -77,6 +77,11 @@ def main():
     ctx.set_option("lane", 0)
     point_target("K2 ms_cyclic BCH(15,7) MS 3 dB fused (warp kernel, option lane = 0)", "ms_cyclic_kernel", c15, 3.0, 8 * M, "MS", 1.0)
     ctx.set_option("lane", -1)
+    c31 = ctx.bch(5, errors=3)
+    point_target("K2s ms_cyclic_lane BCH(31,16) NMS 4 dB fused", "ms_cyclic_lane_kernel", c31, 4.0, 4 * M, "NMS")
+    ctx.set_option("lane", 0)
+    point_target("K2 ms_cyclic BCH(31,16) NMS 4 dB fused (warp kernel, option lane = 0)", "ms_cyclic_kernel", c31, 4.0, 4 * M, "NMS")
+    ctx.set_option("lane", -1)
     c127 = ctx.bch(7, errors=10)
     point_target("K2 ms_cyclic BCH(127,64) NMS 5 dB fused", "ms_cyclic_kernel", c127, 5.0, M // 4, "NMS")
     point_target("K2q ms_cyclic_q BCH(127,64) NMS_Q 5 dB fused", "ms_cyclic_q_kernel", c127, 5.0, M // 4, "NMS_Q", quant=(8.0, 31, 31))
