@@ -41,6 +41,9 @@
 #define CCGPU_MS_YREG_BUDGET 28  /* messages + y values a lane keeps in registers (one-row-per-lane shapes), see YN; \
    measured on BCH(63,36), W = 18: y of 0 / 6 / 10 / 18 taps -> 2.25e8 / 2.28e8 / 2.30e8 / 2.26e8 frames/s */
 #endif
+#ifndef CCGPU_MS_YREG_RPL2
+#define CCGPU_MS_YREG_RPL2 4  /* y values per row kept in registers by the two-rows-per-lane shapes: BCH(127,64) NMS 5 dB 0 -> 4.278e7 frames/s, 4 -> 4.324e7, 6 -> 4.260e7 */
+#endif
 #ifndef CCGPU_MS_CAP_W
 #define CCGPU_MS_CAP_W 30  /* message registers per lane up to which the 64-register cap is applied */
 #endif
@@ -182,7 +185,8 @@ __global__ void __launch_bounds__(kMsThreads, ms_min_blocks<S, VNQ>()) ms_cyclic
   // y of a row's edges is loop invariant: the first YN of them stay in registers (one shared-memory load less per
   // edge and iteration) as far as the 64-register budget of 8 resident CTAs per SM allows
   constexpr int YCAP = CCGPU_MS_YREG_BUDGET - W;
-  constexpr int YN = (!SC && !SPA && !WRAP && RPL == 1 && YCAP > 0) ? ((YCAP < W ? YCAP : W) & ~1) : 0;
+  constexpr int YN = (!SC && !SPA && !WRAP && RPL == 1 && YCAP > 0) ? ((YCAP < W ? YCAP : W) & ~1)
+                     : (!SC && !SPA && !WRAP && RPL == 2 && FPW == 1) ? (CCGPU_MS_YREG_RPL2 & ~1) : 0;
   constexpr bool YREG = YN > 0;
   // ordered column sums: with one row per lane the read-modify-write chain goes through VOLATILE accesses, which
   // ptxas keeps in program order, instead of one __syncwarp per tap (ptxas proves the warp converged and turns

@@ -54,6 +54,18 @@
 #define CCGPU_MS_CTA_SMALL_MINBLK 6  /* ... are compiled for this many CTAs per SM */
 #endif
 
+#ifndef CCGPU_MS_CTA_YN
+#define CCGPU_MS_CTA_YN 16  /* y values of a row the small gather shapes keep in registers.  Measured on the 127-row \
+   BCH(127,64), NMS 5 dB: 0 -> 2.037e7 frames/s, 8 -> 2.119e7, 16 -> 2.185e7 (79 registers, no spills), 22 -> 2.078e7 \
+   (spills), 30 -> 1.953e7 */
+#endif
+#ifndef CCGPU_MS_CTA_BIG_YN
+#define CCGPU_MS_CTA_BIG_YN 24  /* the same for the shapes with more than CCGPU_MS_CTA_SMALL_W messages per thread. \
+   Measured on BCH(255,131), NMS 4 dB, four CTAs per SM (128 registers): 0 -> 3.704e6 frames/s, 8 -> 3.69e6, 16 -> 3.73e6, \
+   24 -> 3.80e6 (32 bytes spilled), 32 -> 3.07e6 (104 bytes spilled); three CTAs per SM (168 registers): 32 -> 3.73e6, \
+   48 -> 3.74e6, 68 -> 3.20e6 */
+#endif
+
 namespace ccgpu {
 
 // the two-rows-per-thread (wrap-around) shapes and the self-correcting flavour need more than 128 registers
@@ -114,6 +126,8 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyc
   constexpr bool GATHER = S::GATHER;
   constexpr bool DUP = GATHER && WRAP;     // y / S mirrored behind entry N - 1: no wrap test in the row phase
   constexpr int XS = S::XS, YW = S::YW;
+  constexpr int YWANT = W <= CCGPU_MS_CTA_SMALL_W ? CCGPU_MS_CTA_YN : CCGPU_MS_CTA_BIG_YN;
+  constexpr int YN = (YWANT > 0 && GATHER && RPL == 1 && VN != VN_SC) ? (YWANT < W ? YWANT : W) : 0;
   using T = typename S::taps;
   extern __shared__ float xdyn[];  // GATHER: 32 guard floats, then W arrays of XS floats (rows, then a zero guard band)
   float *const xs = xdyn + 32;
@@ -263,6 +277,14 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyc
       __syncthreads();
     }
 
+    // y of the first YN taps of this thread's row is loop invariant: keep it in registers (the shapes with few messages
+    // per thread have the registers to spare; one shared-memory load less per such edge and iteration)
+    float yreg[YN > 0 ? YN : 1];
+    if (YN > 0 && !quick) {
+#pragma unroll
+      for (int j = 0; j < YN; ++j) yreg[j] = yrow[0][T::get(j)];
+    }
+
     int it = 0;
     bool stop = quick;
     for (; !quick; ++it) {
@@ -277,7 +299,7 @@ __global__ void __launch_bounds__(S::THREADS, ms_cta_min_blocks<S, VN>()) ms_cyc
           int off = T::get(j);
           if (WRAP && !DUP && row[i] + off >= N) off -= N;
           const float s = yrow[i][YW + off];
-          const float yy = yrow[i][off];
+          const float yy = (YN > 0 && j < YN) ? yreg[j < YN ? j : 0] : yrow[i][off];
           float e = __fsub_rn(s, r[i][j]);  // scalar adds here: the packed FADD2 form of ms_cyclic.cuh needs aligned
           if (VN == VN_2D) e = __fmul_rn(p.beta_f, e);  // register pairs and spills at this kernel's 128-register budget
           float q = __fadd_rn(e, yy);
