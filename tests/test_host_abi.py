@@ -26,6 +26,18 @@ def test_header_symbols_exported():
     assert ctypes.sizeof(_lib.MsParams) == 48
 
 
+def test_every_entry_point_is_documented():
+    """INTEGRATION.md's table names every exported entry point next to the reference interface it replaces (or says that
+    it has none), and include/ccgpu.h cites a reference file:line for the entry points that have a counterpart"""
+    with open(os.path.join(ROOT, "INTEGRATION.md")) as f:
+        doc = f.read()
+    missing = [name for name in _lib.EXPORTS if "`%s`" % name[len("ccgpu_"):] not in doc]
+    assert not missing, missing
+    with open(os.path.join(ROOT, "include", "ccgpu.h")) as f:
+        header = f.read()
+    assert len(re.findall(r"[a-z_]+\.(?:h|c\+\+):\d+", header)) >= 30   # file:line citations of the reference
+
+
 def test_no_device_is_loud():
     """no CUDA device here: creating a context must fail, there is no CPU fallback"""
     import torch
