@@ -38,6 +38,23 @@ def test_every_entry_point_is_documented():
     assert len(re.findall(r"[a-z_]+\.(?:h|c\+\+):\d+", header)) >= 30   # file:line citations of the reference
 
 
+def test_generated_shapes_header_is_current():
+    """csrc/ms_shapes_generated.h is committed (the library build does not run the generator): it must be what
+    csrc/gen_ms_shapes.py produces, i.e. the tap offsets of every compiled kernel shape are those of the reference's H()
+    (cyclic.h:346-359) recomputed from the BCH generator polynomial"""
+    import importlib.util
+    src = os.path.join(ROOT, "channelcoding_b200", "csrc", "gen_ms_shapes.py")
+    spec = importlib.util.spec_from_file_location("gen_ms_shapes", src)
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    with open(os.path.join(ROOT, "channelcoding_b200", "csrc", "ms_shapes_generated.h")) as f:
+        committed = f.read()
+    assert gen.main(path=None) == committed
+    # and the taps the generator derives are the reference's: row 0 of H() of the golden codes
+    n, k, taps = gen.bch_h_taps(6, 5)
+    assert (n, k) == (63, 27) and taps == [0, 5, 6, 8, 9, 15, 17, 18, 22, 24, 25, 26, 29, 31, 33, 34, 35, 36]
+
+
 def test_no_device_is_loud():
     """no CUDA device here: creating a context must fail, there is no CPU fallback"""
     import torch
